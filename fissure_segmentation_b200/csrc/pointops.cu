@@ -1,0 +1,276 @@
+// pointops_cuda operator family behind models/pointtransformer/pointops.py (upstream
+// POSTECH-CVLab/point-transformer lib/pointops, not vendored by the reference). knnquery lives in
+// knn.cu; this file holds farthest point sampling and the gather-style operators, plus the fused
+// Adam step and the library's version / error-string entry points.
+#include "fs_common.cuh"
+
+namespace {
+
+constexpr int FPS_THREADS = 1024;
+
+// One CTA per segment. Each round: every thread relaxes tmp[j] = min(tmp[j], |p_j - p_last|^2) for its
+// points and proposes its farthest point; a two-level (shuffle, shared) arg-max picks the winner,
+// ties -> lower index.
+__global__ void __launch_bounds__(FPS_THREADS)
+fps_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ offset, const int32_t* __restrict__ new_offset,
+           float* __restrict__ tmp, int32_t* __restrict__ idx) {
+    __shared__ float s_d[32];
+    __shared__ int s_i[32];
+    __shared__ int s_last;
+    const int s = blockIdx.x;
+    const int start = s == 0 ? 0 : offset[s - 1];
+    const int end = offset[s];
+    const int ostart = s == 0 ? 0 : new_offset[s - 1];
+    const int m = new_offset[s] - ostart;
+    if (m <= 0 || end <= start) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int last = start;
+    if (threadIdx.x == 0) idx[ostart] = start;
+    for (int r = 1; r < m; ++r) {
+        const float lx = __ldg(xyz + 3ll * last), ly = __ldg(xyz + 3ll * last + 1), lz = __ldg(xyz + 3ll * last + 2);
+        float bd = -1.f;
+        int bi = FS_IDX_PAD;
+        for (int j = start + threadIdx.x; j < end; j += FPS_THREADS) {
+            const float dx = __ldg(xyz + 3ll * j) - lx, dy = __ldg(xyz + 3ll * j + 1) - ly, dz = __ldg(xyz + 3ll * j + 2) - lz;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float t = fminf(tmp[j], d);
+            tmp[j] = t;
+            if (t > bd) { bd = t; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(FS_FULL_MASK, bd, o);
+            const int oi = __shfl_xor_sync(FS_FULL_MASK, bi, o);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0) { s_d[warp] = bd; s_i[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            bd = s_d[lane]; bi = s_i[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(FS_FULL_MASK, bd, o);
+                const int oi = __shfl_xor_sync(FS_FULL_MASK, bi, o);
+                if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (lane == 0) { s_last = bi; idx[ostart + r] = bi; }
+        }
+        __syncthreads();
+        last = s_last;
+        __syncthreads();
+    }
+}
+
+__global__ void grouping_fwd_kernel(long long total, int nsample, int c, const float* __restrict__ in,
+                                    const int32_t* __restrict__ idx, float* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long ms = e / c;
+        const int ch = (int)(e - ms * c);
+        out[e] = __ldg(in + (long long)__ldg(idx + ms) * c + ch);
+    }
+}
+__global__ void grouping_bwd_kernel(long long total, int nsample, int c, const float* __restrict__ go,
+                                    const int32_t* __restrict__ idx, float* __restrict__ gi) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long ms = e / c;
+        const int ch = (int)(e - ms * c);
+        atomicAdd(gi + (long long)__ldg(idx + ms) * c + ch, __ldg(go + e));
+    }
+}
+__global__ void interpolation_fwd_kernel(long long total, int c, int k, const float* __restrict__ in,
+                                         const int32_t* __restrict__ idx, const float* __restrict__ w,
+                                         float* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long n = e / c;
+        const int ch = (int)(e - n * c);
+        float acc = 0.f;
+        for (int i = 0; i < k; ++i) acc = fmaf(__ldg(w + n * k + i), __ldg(in + (long long)__ldg(idx + n * k + i) * c + ch), acc);
+        out[e] = acc;
+    }
+}
+__global__ void interpolation_bwd_kernel(long long total, int c, int k, const float* __restrict__ go,
+                                         const int32_t* __restrict__ idx, const float* __restrict__ w,
+                                         float* __restrict__ gi) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long n = e / c;
+        const int ch = (int)(e - n * c);
+        const float g = __ldg(go + e);
+        for (int i = 0; i < k; ++i) atomicAdd(gi + (long long)__ldg(idx + n * k + i) * c + ch, g * __ldg(w + n * k + i));
+    }
+}
+__global__ void subtraction_fwd_kernel(long long total, int nsample, int c, const float* __restrict__ in1,
+                                       const float* __restrict__ in2, const int32_t* __restrict__ idx,
+                                       float* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long ns = e / c;
+        const int ch = (int)(e - ns * c);
+        const long long n = ns / nsample;
+        out[e] = __ldg(in1 + n * c + ch) - __ldg(in2 + (long long)__ldg(idx + ns) * c + ch);
+    }
+}
+__global__ void subtraction_bwd_kernel(long long total, int nsample, int c, const int32_t* __restrict__ idx,
+                                       const float* __restrict__ go, float* __restrict__ g1, float* __restrict__ g2) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long ns = e / c;
+        const int ch = (int)(e - ns * c);
+        const long long n = ns / nsample;
+        const float g = __ldg(go + e);
+        atomicAdd(g1 + n * c + ch, g);
+        atomicAdd(g2 + (long long)__ldg(idx + ns) * c + ch, -g);
+    }
+}
+__global__ void aggregation_fwd_kernel(long long total, int nsample, int c, int w_c, const float* __restrict__ in,
+                                       const float* __restrict__ pos, const float* __restrict__ w,
+                                       const int32_t* __restrict__ idx, float* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long n = e / c;
+        const int ch = (int)(e - n * c);
+        const int wc = ch % w_c;
+        float acc = 0.f;
+        for (int s = 0; s < nsample; ++s) {
+            const long long ns = n * nsample + s;
+            acc = fmaf(__ldg(in + (long long)__ldg(idx + ns) * c + ch) + __ldg(pos + ns * c + ch), __ldg(w + ns * w_c + wc), acc);
+        }
+        out[e] = acc;
+    }
+}
+__global__ void aggregation_bwd_kernel(long long total, int nsample, int c, int w_c, const float* __restrict__ in,
+                                       const float* __restrict__ pos, const float* __restrict__ w,
+                                       const int32_t* __restrict__ idx, const float* __restrict__ go,
+                                       float* __restrict__ gi, float* __restrict__ gp, float* __restrict__ gw) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long n = e / c;
+        const int ch = (int)(e - n * c);
+        const int wc = ch % w_c;
+        const float g = __ldg(go + e);
+        for (int s = 0; s < nsample; ++s) {
+            const long long ns = n * nsample + s;
+            const long long src = (long long)__ldg(idx + ns) * c + ch;
+            const float wv = __ldg(w + ns * w_c + wc);
+            atomicAdd(gi + src, g * wv);
+            gp[ns * c + ch] = g * wv;
+            atomicAdd(gw + ns * w_c + wc, g * (__ldg(in + src) + __ldg(pos + ns * c + ch)));
+        }
+    }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2_sqrt, float gscale, const float* __restrict__ dyn) {
+    if (dyn) {  // device-resident [step, lr]: lets a captured CUDA graph replay with a moving step / schedule
+        const float st = __ldg(dyn);
+        lr = __ldg(dyn + 1);
+        bc1 = 1.f - powf(b1, st);
+        bc2_sqrt = sqrtf(1.f - powf(b2, st));
+    }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const float pv = p[e];
+        const float gv = fmaf(wd, pv, g[e] * gscale);
+        const float mv = fmaf(1.f - b1, gv - m[e], m[e]);          // lerp(m, g, 1-b1)
+        const float vv = fmaf(b2, v[e], (1.f - b2) * gv * gv);
+        m[e] = mv;
+        v[e] = vv;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p[e] = pv - (lr / bc1) * (mv / denom);
+    }
+}
+
+int flat_grid(long long total) {
+    long long g = (total + 255) / 256;
+    const long long cap = (long long)FS_NUM_SMS * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int fs_version(void) { return 100; }
+
+extern "C" const char* fs_error_string(int code) {
+    switch (code) {
+        case FS_OK: return "success";
+        case FS_ERR_BAD_ARG: return "fissure_b200: bad argument";
+        case FS_ERR_UNSUPPORTED: return "fissure_b200: unsupported shape or dtype";
+        case FS_ERR_ALIGNMENT: return "fissure_b200: pointer or leading dimension not 16-byte aligned";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "fissure_b200: unknown error";
+}
+
+extern "C" int fs_furthestsampling(int device, fs_stream_t stream_, int b, const float* xyz, const int32_t* offset,
+                                   const int32_t* new_offset, float* tmp, int32_t* idx) {
+    if (!xyz || !offset || !new_offset || !tmp || !idx || b < 0) return FS_ERR_BAD_ARG;
+    if (b == 0) return FS_OK;
+    FS_ENTER(device);
+    fps_kernel<<<b, FPS_THREADS, 0, (cudaStream_t)stream_>>>(xyz, offset, new_offset, tmp, idx);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+#define FLAT_LAUNCH(kernel, total, ...)                                                      \
+    do {                                                                                     \
+        if ((total) <= 0) return FS_OK;                                                      \
+        FS_ENTER(device);                                                                    \
+        kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream_>>>(total, __VA_ARGS__);     \
+        FS_RETURN_IF_LAUNCH_FAILED();                                                        \
+        return FS_OK;                                                                        \
+    } while (0)
+
+extern "C" int fs_grouping_fwd(int device, fs_stream_t stream_, int m, int nsample, int c, const float* in,
+                               const int32_t* idx, float* out) {
+    if (!in || !idx || !out || m < 0 || nsample < 0 || c < 0) return FS_ERR_BAD_ARG;
+    FLAT_LAUNCH(grouping_fwd_kernel, (long long)m * nsample * c, nsample, c, in, idx, out);
+}
+extern "C" int fs_grouping_bwd(int device, fs_stream_t stream_, int m, int nsample, int c, const float* grad_out,
+                               const int32_t* idx, float* grad_in) {
+    if (!grad_out || !idx || !grad_in || m < 0 || nsample < 0 || c < 0) return FS_ERR_BAD_ARG;
+    FLAT_LAUNCH(grouping_bwd_kernel, (long long)m * nsample * c, nsample, c, grad_out, idx, grad_in);
+}
+extern "C" int fs_interpolation_fwd(int device, fs_stream_t stream_, int n, int c, int k, const float* in,
+                                    const int32_t* idx, const float* weight, float* out) {
+    if (!in || !idx || !weight || !out || n < 0 || c < 0 || k < 0) return FS_ERR_BAD_ARG;
+    FLAT_LAUNCH(interpolation_fwd_kernel, (long long)n * c, c, k, in, idx, weight, out);
+}
+extern "C" int fs_interpolation_bwd(int device, fs_stream_t stream_, int n, int c, int k, const float* grad_out,
+                                    const int32_t* idx, const float* weight, float* grad_in) {
+    if (!grad_out || !idx || !weight || !grad_in || n < 0 || c < 0 || k < 0) return FS_ERR_BAD_ARG;
+    FLAT_LAUNCH(interpolation_bwd_kernel, (long long)n * c, c, k, grad_out, idx, weight, grad_in);
+}
+extern "C" int fs_subtraction_fwd(int device, fs_stream_t stream_, int n, int nsample, int c, const float* in1,
+                                  const float* in2, const int32_t* idx, float* out) {
+    if (!in1 || !in2 || !idx || !out || n < 0 || nsample < 0 || c < 0) return FS_ERR_BAD_ARG;
+    FLAT_LAUNCH(subtraction_fwd_kernel, (long long)n * nsample * c, nsample, c, in1, in2, idx, out);
+}
+extern "C" int fs_subtraction_bwd(int device, fs_stream_t stream_, int n, int nsample, int c, const int32_t* idx,
+                                  const float* grad_out, float* grad_in1, float* grad_in2) {
+    if (!idx || !grad_out || !grad_in1 || !grad_in2 || n < 0 || nsample < 0 || c < 0) return FS_ERR_BAD_ARG;
+    FLAT_LAUNCH(subtraction_bwd_kernel, (long long)n * nsample * c, nsample, c, idx, grad_out, grad_in1, grad_in2);
+}
+extern "C" int fs_aggregation_fwd(int device, fs_stream_t stream_, int n, int nsample, int c, int w_c, const float* in,
+                                  const float* pos, const float* weight, const int32_t* idx, float* out) {
+    if (!in || !pos || !weight || !idx || !out || n < 0 || nsample < 0 || c < 0 || w_c <= 0) return FS_ERR_BAD_ARG;
+    FLAT_LAUNCH(aggregation_fwd_kernel, (long long)n * c, nsample, c, w_c, in, pos, weight, idx, out);
+}
+extern "C" int fs_aggregation_bwd(int device, fs_stream_t stream_, int n, int nsample, int c, int w_c, const float* in,
+                                  const float* pos, const float* weight, const int32_t* idx, const float* grad_out,
+                                  float* grad_in, float* grad_pos, float* grad_weight) {
+    if (!in || !pos || !weight || !idx || !grad_out || !grad_in || !grad_pos || !grad_weight || n < 0 || nsample < 0 ||
+        c < 0 || w_c <= 0)
+        return FS_ERR_BAD_ARG;
+    FLAT_LAUNCH(aggregation_bwd_kernel, (long long)n * c, nsample, c, w_c, in, pos, weight, idx, grad_out, grad_in,
+                grad_pos, grad_weight);
+}
+
+extern "C" int fs_adam_step(int device, fs_stream_t stream_, float* param, const float* grad, float* exp_avg,
+                            float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, int step, float grad_scale, const float* dyn_step_lr) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0 || (step <= 0 && !dyn_step_lr)) return FS_ERR_BAD_ARG;
+    if (n == 0) return FS_OK;
+    FS_ENTER(device);
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    adam_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream_>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                               weight_decay, bc1, bc2_sqrt, grad_scale, dyn_step_lr);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}

@@ -1,0 +1,116 @@
+"""Data-parallel harness: one process per GPU, batch-sharded clouds, gradient all-reduce overlapped
+with backward. The reference has no distributed code; this sits beside its trainer.
+
+Parameters and gradients live in two flat fp32 buffers (each nn.Parameter is a view). Gradients are
+grouped into a few buckets in reverse registration order (the order backward produces them); when the
+last gradient of a bucket has been accumulated, an asynchronous all-reduce (NCCL over NVLink on GPUs,
+gloo in the CPU tests) is issued on that bucket while the rest of backward is still running. BatchNorm
+statistics stay per rank (standard DDP semantics).
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class FlatDataParallel:
+    def __init__(self, module, n_buckets=2, process_group=None, broadcast=True):
+        self.module = module
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("module has no trainable parameters")
+        dev, dt = params[0].device, params[0].dtype
+        # reverse registration order ~ order in which backward finishes the gradients
+        order = list(reversed(params))
+        total = sum(p.numel() for p in order)
+        self.flat_param = torch.empty(total, dtype=dt, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=dt, device=dev)
+        self._slices = []
+        off = 0
+        with torch.no_grad():
+            for p in order:
+                n = p.numel()
+                self.flat_param[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat_param[off:off + n].view_as(p)
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+                self._slices.append((off, n))
+                off += n
+        self.params = order
+        # contiguous buckets of roughly equal size
+        n_buckets = max(1, min(n_buckets, len(order)))
+        target = total / n_buckets
+        self.buckets = []          # (start, end, n_params)
+        self._bucket_of = {}
+        start, count, b = 0, 0, 0
+        for i, (o, n) in enumerate(self._slices):
+            self._bucket_of[id(order[i])] = b
+            count += 1
+            end = o + n
+            if (end - start >= target and b < n_buckets - 1) or i == len(order) - 1:
+                self.buckets.append((start, end, count))
+                start, count, b = end, 0, b + 1
+        self._ready = [0] * len(self.buckets)
+        self._works = []
+        if self.world > 1:
+            if broadcast:
+                dist.broadcast(self.flat_param, src=0, group=self.group)
+            for p in order:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def _hook(self, p):
+        b = self._bucket_of[id(p)]
+        self._ready[b] += 1
+        if self._ready[b] == self.buckets[b][2]:
+            s, e, _ = self.buckets[b]
+            self._works.append(dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.SUM, group=self.group,
+                                               async_op=True))
+
+    def __call__(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        for p in self.params:      # keep the views attached even if something set .grad to None
+            if p.grad is None:
+                o, n = self._slices[self.params.index(p)]
+                p.grad = self.flat_grad[o:o + n].view_as(p)
+
+    def finish_backward(self):
+        """Wait for the outstanding bucket all-reduces; flat_grad then holds the SUM over ranks
+        (the 1/world average is folded into the optimiser's grad_scale)."""
+        if self.world > 1 and sum(self._ready) != sum(b[2] for b in self.buckets):
+            # parameters that received no gradient this step: reduce whatever has not been sent
+            for b, (s, e, cnt) in enumerate(self.buckets):
+                if self._ready[b] != cnt:
+                    self._works.append(dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.SUM, group=self.group,
+                                                       async_op=True))
+        for w in self._works:
+            w.wait()
+        self._works = []
+        self._ready = [0] * len(self.buckets)
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr, weight_decay) semantics (model_trainer.py:57) as one fused kernel over the
+    flat buffers of FlatDataParallel. Step count and learning rate live on the device so the whole
+    training step can be captured in a CUDA graph."""
+
+    def __init__(self, dp, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
+        self.dp = dp
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(dp.flat_param)
+        self.exp_avg_sq = torch.zeros_like(dp.flat_param)
+        self.dyn = torch.tensor([0.0, lr], dtype=torch.float32, device=dp.flat_param.device)   # [step, lr]
+        self._inc = torch.tensor([1.0, 0.0], dtype=torch.float32, device=dp.flat_param.device)
+
+    def set_lr(self, lr):
+        self.lr = lr
+        self.dyn[1] = lr
+
+    def step(self):
+        self.dyn.add_(self._inc)
+        _lib.call("fs_adam_step", self.dp.flat_param, self.dp.flat_param, self.dp.flat_grad, self.exp_avg,
+                  self.exp_avg_sq, self.dp.flat_param.numel(), float(self.lr), float(self.betas[0]),
+                  float(self.betas[1]), float(self.eps), float(self.weight_decay), 0, 1.0 / self.dp.world, self.dyn)

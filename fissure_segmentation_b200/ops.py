@@ -1,0 +1,306 @@
+"""Host-side operators over the C ABI: kNN graph build, fused EdgeConv (autograd), nearest-neighbour
+reduction for Chamfer. Tensors are torch CUDA tensors; the arithmetic runs in libfissure_b200.so.
+
+Layout convention: "point-major" tables of shape (P, C) with P = B*N rows (row = b*N + n) and unit
+stride along C. The reference's (B, C, N) tensors are converted at the module boundary only.
+"""
+import torch
+
+from . import _lib
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class KnnGraph:
+    """A kNN graph of B clouds with N points: int32 neighbour indices (B, N, k), local to the cloud,
+    plus the lazily built reverse (incoming-edge) graph used by the EdgeConv backward."""
+
+    __slots__ = ("idx", "B", "N", "k", "_rev")
+
+    def __init__(self, idx):
+        assert idx.dtype == torch.int32 and idx.dim() == 3 and idx.is_contiguous()
+        self.idx = idx
+        self.B, self.N, self.k = idx.shape
+        self._rev = None
+
+    @classmethod
+    def from_reference(cls, idx64):
+        """Accept the reference's (B, N, k) int64 graph (models/dgcnn.py:28-29 fixed_knn_graph)."""
+        return cls(idx64.to(torch.int32).contiguous())
+
+    def reverse(self):
+        if self._rev is None:
+            P = self.B * self.N
+            rev_ptr = torch.empty(P + 1, dtype=torch.int32, device=self.idx.device)
+            rev_src = torch.empty(P * self.k, dtype=torch.int32, device=self.idx.device)
+            _lib.call("fs_reverse_graph", self.idx, self.idx, self.B, self.N, self.k, rev_ptr, rev_src)
+            self._rev = (rev_ptr, rev_src)
+        return self._rev
+
+
+# ------------------------------------------------------------------------------------------- kNN
+
+def _check_k(k, self_loop, N):
+    kk = k + (0 if self_loop else 1)
+    if kk > N:
+        # torch.topk raises the same way in the reference (general_utils.py:320)
+        raise RuntimeError("selected index k out of range: k=%d (+%d) > N=%d" % (k, kk - k, N))
+    if kk > _lib.FS_MAX_K + 1:
+        raise RuntimeError("k=%d exceeds the supported maximum of %d" % (k, _lib.FS_MAX_K))
+
+
+def knn_coords(x, k, self_loop=False, diag_zero=True, return_dist=False):
+    """kNN on the first three channels of x (B, C>=3, N), any strides. Returns int32 (B, N, k)."""
+    B, _, N = x.shape
+    _check_k(k, self_loop, N)
+    if x.dtype != torch.float32:
+        x = x.float()
+    idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
+    dist = torch.empty(B, N, k, dtype=torch.float32, device=x.device) if return_dist else None
+    _lib.call("fs_knn3d", x, x, x.stride(0), x.stride(1), x.stride(2), B, N, k, int(self_loop), int(diag_zero),
+              idx, dist)
+    return (idx, dist) if return_dist else idx
+
+
+def knn_features(feat, B, N, k, self_loop=False, diag_zero=True, return_dist=False):
+    """Exact FP32 kNN on a point-major feature table (B*N, C) (row stride arbitrary)."""
+    _check_k(k, self_loop, N)
+    if feat.dtype != torch.float32:
+        feat = feat.float()
+    if feat.stride(1) != 1:
+        feat = feat.contiguous()
+    C = feat.shape[1]
+    idx = torch.empty(B, N, k, dtype=torch.int32, device=feat.device)
+    dist = torch.empty(B, N, k, dtype=torch.float32, device=feat.device) if return_dist else None
+    ws = torch.empty(B * N, dtype=torch.float32, device=feat.device)
+    _lib.call("fs_knn_feat", feat, feat, feat.stride(0), B, N, C, k, int(self_loop), int(diag_zero), idx, dist, ws)
+    return (idx, dist) if return_dist else idx
+
+
+def to_point_major(x):
+    """(B, C, N) -> contiguous (B*N, C)."""
+    B, C, N = x.shape
+    return x.transpose(1, 2).reshape(B * N, C)
+
+
+def knn_any(x, k, self_loop=False, diag_zero=True, return_dist=False):
+    """kNN over all channels of x (B, C, N): 3-D kernel for C == 3, feature kernel otherwise."""
+    B, C, N = x.shape
+    if C == 3:
+        return knn_coords(x, k, self_loop, diag_zero, return_dist)
+    return knn_features(to_point_major(x.float()), B, N, k, self_loop, diag_zero, return_dist)
+
+
+# ------------------------------------------------------------------------------------------- EdgeConv
+
+def _bn_coef(table_ref, stats, count, gamma, beta, running_mean, running_var, nbt, training, Cp, eps, momentum):
+    coef = torch.empty(4 * Cp, dtype=torch.float32, device=table_ref.device)
+    if training:
+        _lib.call("fs_bn_finalize", table_ref, stats, float(count), Cp, gamma, beta, eps, momentum, coef,
+                  running_mean, running_var, nbt)
+    else:
+        _lib.call("fs_bn_coef_eval", table_ref, Cp, gamma, beta, running_mean, running_var, eps, coef)
+    return coef
+
+
+class _EdgeConvFn(torch.autograd.Function):
+    """Single-layer EdgeConv on the per-point table T = [a | b]:
+    out_i = LeakyReLU(BN(max_j (a_j + b_i))), models/dgcnn.py:226-243 with a one-layer shared MLP."""
+
+    @staticmethod
+    def forward(ctx, table, gamma, beta, graph, running_mean, running_var, nbt, training, eps, momentum):
+        idx = graph.idx
+        B, N, k = graph.B, graph.N, graph.k
+        P, Cp = B * N, table.shape[1] // 2
+        dev = table.device
+        dt = _lib.dtype_code(table)
+        gamma32, beta32 = gamma.detach().float(), beta.detach().float()
+        sel = torch.empty(P, Cp, dtype=torch.float32, device=dev)
+        arg = torch.empty(P, Cp, dtype=torch.uint8, device=dev)
+        need_grad = any(ctx.needs_input_grad[:3])
+        sy = torch.empty(P, Cp, dtype=torch.float32, device=dev) if (training and need_grad) else None
+        stats = torch.zeros(3 * Cp, dtype=torch.float64, device=dev) if training else None
+        _lib.call("fs_edgeconv_gather", table, table, dt, table.stride(0), idx, B, N, k, Cp, gamma32, sel, arg, sy,
+                  stats)
+        coef = _bn_coef(table, stats, P * k, gamma32, beta32, running_mean, running_var, nbt, training, Cp, eps,
+                        momentum)
+        out = torch.empty(P, Cp, dtype=table.dtype, device=dev)
+        _lib.call("fs_edgeconv_apply", table, sel, table, dt, table.stride(0), P, Cp, coef, out, _lib.dtype_code(out),
+                  out.stride(0))
+        ctx.graph = graph
+        ctx.training = training
+        ctx.save_for_backward(table, sel, arg, sy, coef)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        table, sel, arg, sy, coef = ctx.saved_tensors
+        graph = ctx.graph
+        B, N, k = graph.B, graph.N, graph.k
+        P, Cp = B * N, table.shape[1] // 2
+        dev = table.device
+        dt = _lib.dtype_code(table)
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        d = torch.empty(P, Cp, dtype=torch.float32, device=dev)
+        dgb = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+        _lib.call("fs_edgeconv_bwd_reduce", table, g, _lib.dtype_code(g), g.stride(0), sel, table, dt, table.stride(0),
+                  P, Cp, coef, d, dgb)
+        dT = torch.empty(P, 2 * Cp, dtype=torch.float32, device=dev)
+        dgam_dbet = torch.empty(2 * Cp, dtype=torch.float32, device=dev)
+        if ctx.training:
+            rev_ptr, rev_src = graph.reverse()
+        else:
+            rev_ptr = rev_src = None
+        _lib.call("fs_edgeconv_bwd_point", table, d, sy, table, dt, table.stride(0), rev_ptr, rev_src, P, k, Cp, coef,
+                  dgb, float(P * k), int(ctx.training), dT, dgam_dbet)
+        _lib.call("fs_edgeconv_bwd_route", table, d, arg, graph.idx, B, N, k, Cp, coef, dT)
+        if dT.dtype != table.dtype:
+            dT = dT.to(table.dtype)
+        return dT, dgam_dbet[:Cp], dgam_dbet[Cp:], None, None, None, None, None, None, None
+
+
+def edgeconv_fused(table, gamma, beta, graph, running_mean, running_var, nbt, training, out=None,
+                   eps=BN_EPS, momentum=BN_MOMENTUM):
+    """table (P, 2*Cp) fp32/bf16 contiguous rows; returns (P, Cp) in table.dtype (or writes `out`)."""
+    assert table.stride(1) == 1
+    if not torch.is_grad_enabled() and not training:
+        # inference: single fused pass, nothing saved
+        B, N, k = graph.B, graph.N, graph.k
+        P, Cp = B * N, table.shape[1] // 2
+        coef = _bn_coef(table, None, 1, gamma.detach().float(), beta.detach().float(), running_mean, running_var,
+                        None, False, Cp, eps, momentum)
+        if out is None:
+            out = torch.empty(P, Cp, dtype=table.dtype, device=table.device)
+        _lib.call("fs_edgeconv_fused_eval", table, table, _lib.dtype_code(table), table.stride(0), graph.idx, B, N, k,
+                  Cp, coef, out, _lib.dtype_code(out), out.stride(0), None)
+        return out
+    return _EdgeConvFn.apply(table, gamma, beta, graph, running_mean, running_var, nbt, training, eps, momentum)
+
+
+class _EdgeBuildFn(torch.autograd.Function):
+    """Y[(i,t)] = a[idx[i,t]] + b[i]: first layer of a two-layer EdgeConv as a materialised edge tensor."""
+
+    @staticmethod
+    def forward(ctx, table, graph, out_dtype):
+        B, N, k = graph.B, graph.N, graph.k
+        P, Cp = B * N, table.shape[1] // 2
+        y = torch.empty(P * k, Cp, dtype=out_dtype, device=table.device)
+        _lib.call("fs_edge_build", table, table, _lib.dtype_code(table), table.stride(0), graph.idx, B, N, k, Cp, y,
+                  _lib.dtype_code(y))
+        ctx.graph = graph
+        ctx.table_dtype = table.dtype
+        ctx.Cp = Cp
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        graph = ctx.graph
+        B, N, k = graph.B, graph.N, graph.k
+        if dy.dtype not in (torch.float32, torch.bfloat16):
+            dy = dy.float()
+        dy = dy.contiguous()
+        dT = torch.zeros(B * N, 2 * ctx.Cp, dtype=torch.float32, device=dy.device)
+        _lib.call("fs_edge_build_bwd", dy, dy, _lib.dtype_code(dy), graph.idx, B, N, k, ctx.Cp, dT)
+        return dT.to(ctx.table_dtype), None, None
+
+
+def edge_build(table, graph, out_dtype=None):
+    return _EdgeBuildFn.apply(table, graph, out_dtype or table.dtype)
+
+
+class _EdgeReduceFn(torch.autograd.Function):
+    """out_i = LeakyReLU(BN(max_t Z[(i,t)])) on a materialised edge tensor Z (P*k, Cp): BatchNorm2d batch
+    statistics over all edges, LeakyReLU(0.2) and max over k (models/dgcnn.py:237-241) in one reduction."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, k, running_mean, running_var, nbt, training, eps, momentum):
+        P, Cp = z.shape[0] // k, z.shape[1]
+        dev = z.device
+        gamma32, beta32 = gamma.detach().float(), beta.detach().float()
+        sel = torch.empty(P, Cp, dtype=torch.float32, device=dev)
+        arg = torch.empty(P, Cp, dtype=torch.uint8, device=dev)
+        stats = torch.zeros(3 * Cp, dtype=torch.float64, device=dev) if training else None
+        _lib.call("fs_edge_reduce", z, z, _lib.dtype_code(z), P, k, Cp, gamma32, sel, arg, None, stats)
+        coef = _bn_coef(z, stats, P * k, gamma32, beta32, running_mean, running_var, nbt, training, Cp, eps, momentum)
+        out = torch.empty(P, Cp, dtype=z.dtype, device=dev)
+        _lib.call("fs_edgeconv_apply", z, sel, None, 0, 0, P, Cp, coef, out, _lib.dtype_code(out), out.stride(0))
+        ctx.k = k
+        ctx.training = training
+        ctx.save_for_backward(z, sel, arg, coef)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        z, sel, arg, coef = ctx.saved_tensors
+        k = ctx.k
+        P, Cp = z.shape[0] // k, z.shape[1]
+        dev = z.device
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        d = torch.empty(P, Cp, dtype=torch.float32, device=dev)
+        dgb = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+        _lib.call("fs_edgeconv_bwd_reduce", z, g, _lib.dtype_code(g), g.stride(0), sel, None, 0, 0, P, Cp, coef, d, dgb)
+        dz = torch.empty_like(z)
+        _lib.call("fs_edge_reduce_bwd", z, z, _lib.dtype_code(z), d, arg, P, k, Cp, coef, dgb, float(P * k),
+                  int(ctx.training), dz, _lib.dtype_code(dz))
+        dgb32 = dgb.float()
+        return dz, dgb32[Cp:], dgb32[:Cp], None, None, None, None, None, None, None
+
+
+def edge_reduce(z, gamma, beta, k, running_mean, running_var, nbt, training, eps=BN_EPS, momentum=BN_MOMENTUM):
+    return _EdgeReduceFn.apply(z, gamma, beta, k, running_mean, running_var, nbt, training, eps, momentum)
+
+
+# ------------------------------------------------------------------------------------------- Chamfer
+
+class _ChamferFn(torch.autograd.Function):
+    """chamfer_distance(x, y)[0] with pytorch3d defaults (losses/chamfer_loss.py:19):
+    mean_b [ mean_i min_j |x_i - y_j|^2 + mean_j min_i |x_i - y_j|^2 ]."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        B, N, _ = x.shape
+        M = y.shape[1]
+        dev = x.device
+        dxy = torch.empty(B, N, dtype=torch.float32, device=dev)
+        ixy = torch.empty(B, N, dtype=torch.int32, device=dev)
+        dyx = torch.empty(B, M, dtype=torch.float32, device=dev)
+        iyx = torch.empty(B, M, dtype=torch.int32, device=dev)
+        _lib.call("fs_nn_points", x, x, y, B, N, M, dxy, ixy)
+        _lib.call("fs_nn_points", x, y, x, B, M, N, dyx, iyx)
+        loss = (dxy.sum(dtype=torch.float64) / (N * B) + dyx.sum(dtype=torch.float64) / (M * B)).float()
+        ctx.save_for_backward(x, y, ixy, iyx)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, ixy, iyx = ctx.saved_tensors
+        B, N, _ = x.shape
+        M = y.shape[1]
+        gx = torch.zeros_like(x)
+        gy = torch.zeros_like(y)
+        g = g.float().contiguous()
+        _lib.call("fs_chamfer_bwd", x, x, y, ixy, B, N, M, 1.0 / (N * B), g, gx, gy)
+        _lib.call("fs_chamfer_bwd", x, y, x, iyx, B, M, N, 1.0 / (M * B), g, gy, gx)
+        return gx, gy
+
+
+def chamfer_distance(x, y):
+    """x (B, N, 3), y (B, M, 3) float32 CUDA tensors -> scalar loss."""
+    return _ChamferFn.apply(x.float().contiguous(), y.float().contiguous())
+
+
+def nn_points(x, y):
+    """Nearest neighbour in y of every point of x: (squared distance (B, N), index int32 (B, N))."""
+    x, y = x.float().contiguous(), y.float().contiguous()
+    B, N, _ = x.shape
+    d = torch.empty(B, N, dtype=torch.float32, device=x.device)
+    i = torch.empty(B, N, dtype=torch.int32, device=x.device)
+    _lib.call("fs_nn_points", x, x, y, B, N, y.shape[1], d, i)
+    return d, i

@@ -1,0 +1,71 @@
+"""Drop-in for the `pointops_cuda` extension module imported at
+models/pointtransformer/pointops.py:13 (upstream POSTECH-CVLab/point-transformer lib/pointops).
+
+Same function names and positional signatures as the call sites in pointops.py; arguments are
+contiguous CUDA tensors (float32 / int32), outputs are pre-allocated by the caller, nothing is
+returned, errors raise. Register it with
+    sys.modules['pointops_cuda'] = fissure_segmentation_b200.pointops_cuda
+(or keep the top-level `pointops_cuda.py` of this repository on the path).
+"""
+import torch
+
+from . import _lib
+
+
+def _f32(t):
+    assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32, "expected a contiguous CUDA float32 tensor"
+    return t
+
+
+def _i32(t):
+    assert t.is_cuda and t.is_contiguous() and t.dtype == torch.int32, "expected a contiguous CUDA int32 tensor"
+    return t
+
+
+def furthestsampling_cuda(b, n_max, xyz, offset, new_offset, tmp, idx):  # pointops.py:35
+    _lib.call("fs_furthestsampling", xyz, int(b), _f32(xyz), _i32(offset), _i32(new_offset), _f32(tmp), _i32(idx))
+
+
+def knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):  # pointops.py:59
+    _lib.call("fs_knnquery", xyz, int(m), int(nsample), _f32(xyz), _f32(new_xyz), _i32(offset), _i32(new_offset),
+              int(offset.shape[0]), _i32(idx), _f32(dist2))
+
+
+def grouping_forward_cuda(m, nsample, c, input, idx, output):  # pointops.py:78
+    _lib.call("fs_grouping_fwd", input, int(m), int(nsample), int(c), _f32(input), _i32(idx), _f32(output))
+
+
+def grouping_backward_cuda(m, nsample, c, grad_output, idx, grad_input):  # pointops.py:94
+    _lib.call("fs_grouping_bwd", grad_output, int(m), int(nsample), int(c), _f32(grad_output), _i32(idx),
+              _f32(grad_input))
+
+
+def subtraction_forward_cuda(n, nsample, c, input1, input2, idx, output):  # pointops.py:139
+    _lib.call("fs_subtraction_fwd", input1, int(n), int(nsample), int(c), _f32(input1), _f32(input2), _i32(idx),
+              _f32(output))
+
+
+def subtraction_backward_cuda(n, nsample, c, idx, grad_output, grad_input1, grad_input2):  # pointops.py:155
+    _lib.call("fs_subtraction_bwd", grad_output, int(n), int(nsample), int(c), _i32(idx), _f32(grad_output),
+              _f32(grad_input1), _f32(grad_input2))
+
+
+def aggregation_forward_cuda(n, nsample, c, w_c, input, position, weight, idx, output):  # pointops.py:174
+    _lib.call("fs_aggregation_fwd", input, int(n), int(nsample), int(c), int(w_c), _f32(input), _f32(position),
+              _f32(weight), _i32(idx), _f32(output))
+
+
+def aggregation_backward_cuda(n, nsample, c, w_c, input, position, weight, idx, grad_output, grad_input,
+                              grad_position, grad_weight):  # pointops.py:192
+    _lib.call("fs_aggregation_bwd", input, int(n), int(nsample), int(c), int(w_c), _f32(input), _f32(position),
+              _f32(weight), _i32(idx), _f32(grad_output), _f32(grad_input), _f32(grad_position), _f32(grad_weight))
+
+
+def interpolation_forward_cuda(n, c, k, input, idx, weight, output):  # pointops.py:236
+    _lib.call("fs_interpolation_fwd", input, int(n), int(c), int(k), _f32(input), _i32(idx), _f32(weight),
+              _f32(output))
+
+
+def interpolation_backward_cuda(n, c, k, grad_output, idx, weight, grad_input):  # pointops.py:252
+    _lib.call("fs_interpolation_bwd", grad_output, int(n), int(c), int(k), _f32(grad_output), _i32(idx),
+              _f32(weight), _f32(grad_input))

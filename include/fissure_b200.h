@@ -1,0 +1,265 @@
+/*
+ * fissure_b200 — C ABI of the B200-native DGCNN EdgeConv hot path.
+ *
+ * Every entry point is what a binding for the reference (kaftanski/fissure-segmentation) would
+ * call in place of the PyTorch expression cited beside it. Citations are file:line in the
+ * reference tree.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller (torch tensors in practice). The library
+ *    never allocates, frees or retains device memory and keeps no mutable global state.
+ *  - `device` is the CUDA ordinal the buffers live on; `stream` is a cudaStream_t of that device.
+ *    Calls are asynchronous with respect to the host and re-entrant (autograd worker threads).
+ *  - Return value: 0 = success, < 0 = fs_status (bad arguments, nothing launched),
+ *    > 0 = cudaError_t of the failed launch. No exceptions, no exit().
+ *  - Point-major tables: a "table" is a row-major matrix with one row per point (row = b*N + n),
+ *    `ld` = row stride in elements. dtype codes: FS_F32 = 0, FS_BF16 = 1.
+ *  - Neighbour indices are int32, local to the cloud (0..N-1), one row of k per point.
+ */
+#ifndef FISSURE_B200_H
+#define FISSURE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fs_stream_t; /* cudaStream_t */
+
+enum fs_status {
+    FS_OK = 0,
+    FS_ERR_BAD_ARG = -1,     /* null pointer, negative size, k out of range ... */
+    FS_ERR_UNSUPPORTED = -2, /* shape or dtype outside the compiled set */
+    FS_ERR_ALIGNMENT = -3    /* pointer / leading dimension not 16-byte aligned */
+};
+
+enum fs_dtype { FS_F32 = 0, FS_BF16 = 1 };
+
+#define FS_MAX_K 127 /* largest k (k+1 when the self match is dropped must be <= 128) */
+
+int fs_version(void);
+/* Static string for a negative fs_status; cudaGetErrorString for positive codes. */
+const char* fs_error_string(int code);
+
+/* ---------------------------------------------------------------- kNN graph build ---------- */
+
+/*
+ * Batched k-nearest-neighbour search on 3-D coordinates (FP32 FMA + warp-shuffle bitonic top-k).
+ * Replaces utils/general_utils.py:315-327 knn() on top of :43-53 pairwise_dist() for C == 3 and
+ * models/dgcnn_opensrc.py:34-40 knn().
+ *   coords           element (b, c, n) at coords[b*batch_stride + c*chan_stride + n*point_stride]
+ *                    (B x C x N reference layout: chan_stride = N, point_stride = 1)
+ *   self_loop        1: the query itself may be returned (knn(..., self_loop=True));
+ *                    0: k+1 are selected and rank 0 is dropped (general_utils.py:317-322)
+ *   diag_zero        1: d(i,i) is forced to 0 (general_utils.py:52); 0: dgcnn_opensrc.knn
+ *   idx  [B*N*k]     int32 neighbour indices, ascending distance, ties -> lower index
+ *   dist2 [B*N*k]    squared distances in the reference's expansion form (nullable)
+ */
+int fs_knn3d(int device, fs_stream_t stream, const float* coords, long long batch_stride,
+             long long chan_stride, long long point_stride, int B, int N, int k, int self_loop,
+             int diag_zero, int32_t* idx, float* dist2);
+
+/*
+ * Exact FP32 k-nearest-neighbour search in C-dimensional feature space on a point-major table.
+ * Replaces the same reference functions for C > 3 (models/dgcnn.py:26 on 64-channel features).
+ *   x [B*N, ldx]     fp32 features, point-major
+ *   sqnorm_ws [B*N]  workspace for the row squared norms
+ */
+int fs_knn_feat(int device, fs_stream_t stream, const float* x, int ldx, int B, int N, int C, int k,
+                int self_loop, int diag_zero, int32_t* idx, float* dist2, float* sqnorm_ws);
+
+/*
+ * Offset-segmented kNN of `new_xyz` in `xyz` (direct squared differences).
+ * Replaces pointops_cuda.knnquery_cuda at models/pointtransformer/pointops.py:59.
+ *   xyz [n,3], new_xyz [m,3], offset [b], new_offset [b]: cumulative int32 segment ends
+ *   idx [m,nsample] int32 GLOBAL row indices into xyz; dist2 [m,nsample] squared distances.
+ *   Segments with fewer than nsample points are padded with (segment start, 1e10).
+ */
+int fs_knnquery(int device, fs_stream_t stream, int m, int nsample, const float* xyz,
+                const float* new_xyz, const int32_t* offset, const int32_t* new_offset, int b,
+                int32_t* idx, float* dist2);
+
+/*
+ * Farthest point sampling per segment. Replaces pointops_cuda.furthestsampling_cuda at
+ * models/pointtransformer/pointops.py:35. `tmp` [n] must be pre-filled with 1e10 by the caller
+ * (pointops.py:32); idx [m_total] receives global row indices, first pick = segment start.
+ */
+int fs_furthestsampling(int device, fs_stream_t stream, int b, const float* xyz,
+                        const int32_t* offset, const int32_t* new_offset, float* tmp, int32_t* idx);
+
+/* ---------------------------------------------------------------- fused EdgeConv ----------- */
+
+/*
+ * Pass 1 of the fused single-layer EdgeConv (models/dgcnn.py:226-243 with one SharedFullyConnected,
+ * i.e. create_neighbor_features :15-36 + Conv2d 1x1 + BatchNorm2d + LeakyReLU(0.2) + max over k).
+ * The per-point table T = X * [W1 ; W2-W1]^T holds a = T[:, :Cp] and b = T[:, Cp:2Cp]; the edge
+ * pre-activation is y(i,j) = a_j + b_i. One gather pass over the k neighbour rows produces
+ *   sel [P,Cp]  f32   max_j a_j where gamma >= 0, min_j a_j where gamma < 0
+ *   arg [P,Cp]  u8    slot (0..k-1) of the selected neighbour
+ *   sy  [P,Cp]  f32   sum_j y(i,j)                      (nullable: eval / no-grad)
+ *   stats [2*Cp+Cp] f64  sum(y-p), sum((y-p)^2) per channel (accumulated with atomics; must be
+ *                     zeroed by the caller) followed by the pivot p (written by the kernel)
+ *                     (nullable: eval mode, no batch statistics)
+ */
+int fs_edgeconv_gather(int device, fs_stream_t stream, const void* table, int dtype, int ld,
+                       const int32_t* idx, int B, int N, int k, int Cp, const float* gamma,
+                       float* sel, uint8_t* arg, float* sy, double* stats);
+
+/*
+ * BatchNorm2d batch statistics -> per-channel affine (torch.nn.BatchNorm2d, models/dgcnn.py:307).
+ *   stats           from fs_edgeconv_gather; count = number of edges B*N*k
+ *   coef [4*Cp] f32 out: mu, invstd, scale = gamma*invstd, shift = beta
+ *   running_mean / running_var / num_batches_tracked updated in place when non-null
+ *   (momentum 0.1, unbiased variance).
+ */
+int fs_bn_finalize(int device, fs_stream_t stream, const double* stats, double count, int Cp,
+                   const float* gamma, const float* beta, float eps, float momentum, float* coef,
+                   float* running_mean, float* running_var, long long* num_batches_tracked);
+
+/* Eval-mode coefficients from running statistics (same coef layout). */
+int fs_bn_coef_eval(int device, fs_stream_t stream, int Cp, const float* gamma, const float* beta,
+                    const float* running_mean, const float* running_var, float eps, float* coef);
+
+/*
+ * Pass 2: out = LeakyReLU_0.2(scale*(sel + b - mu) + beta), written to a point-major table
+ * (fp32 or bf16, leading dimension ld_out — typically a slice of the 192-wide concat buffer).
+ * table == NULL means b = 0 (second layer of a two-layer EdgeConv, where sel comes from
+ * fs_edge_reduce); the same holds for fs_edgeconv_bwd_reduce.
+ */
+int fs_edgeconv_apply(int device, fs_stream_t stream, const float* sel, const void* table,
+                      int dtype, int ld, long long P, int Cp, const float* coef, void* out,
+                      int out_dtype, int ld_out);
+
+/*
+ * Eval-mode single pass: gather + select + folded BN + LeakyReLU straight to `out`.
+ */
+int fs_edgeconv_fused_eval(int device, fs_stream_t stream, const void* table, int dtype, int ld,
+                           const int32_t* idx, int B, int N, int k, int Cp, const float* coef,
+                           void* out, int out_dtype, int ld_out, uint8_t* arg /* nullable */);
+
+/*
+ * Reverse (incoming-edge) graph of a kNN graph, per cloud: counting sort of the B*N*k edges by
+ * target. rev_ptr [B*N+1] global exclusive offsets; rev_src [B*N*k] global source rows.
+ */
+int fs_reverse_graph(int device, fs_stream_t stream, const int32_t* idx, int B, int N, int k,
+                     int32_t* rev_ptr, int32_t* rev_src);
+
+/*
+ * Backward, step 1: d = g * LeakyReLU'(z), dbeta = sum d, dgamma = sum d*yhat.
+ *   g [P, ldg] fp32/bf16 upstream gradient; d [P,Cp] f32 out; dgb [2*Cp] f64 (zeroed by caller).
+ */
+int fs_edgeconv_bwd_reduce(int device, fs_stream_t stream, const void* g, int g_dtype, int ldg,
+                           const float* sel, const void* table, int dtype, int ld, long long P,
+                           int Cp, const float* coef, float* d, double* dgb);
+
+/*
+ * Backward, step 2: BatchNorm-coupled gradient of the per-point table, dT [P, 2*Cp] f32:
+ *   db_i = s*( d_i - k*dbeta/M - (dgamma/M)*invstd*(sy_i - k*mu) )
+ *   da_j = -s*( indeg_j*dbeta/M + (dgamma/M)*invstd*(indeg_j*(a_j-mu) + sum_{i->j} b_i) )
+ * (train_stats = 0: eval-mode BN, da_j = 0 and db_i = s*d_i.)
+ * Also writes dgamma/dbeta as fp32 [2*Cp] (dgamma first) when dgamma_dbeta is non-null.
+ */
+int fs_edgeconv_bwd_point(int device, fs_stream_t stream, const float* d, const float* sy,
+                          const void* table, int dtype, int ld, const int32_t* rev_ptr,
+                          const int32_t* rev_src, long long P, int k, int Cp, const float* coef,
+                          const double* dgb, double count, int train_stats, float* dT,
+                          float* dgamma_dbeta);
+
+/*
+ * Backward, step 3: argmax-routed scatter  dT[idx[i, arg[i,c]], c] += s_c * d[i,c]
+ * (warp-aggregated atomics on the a-half of dT).
+ */
+int fs_edgeconv_bwd_route(int device, fs_stream_t stream, const float* d, const uint8_t* arg,
+                          const int32_t* idx, int B, int N, int k, int Cp, const float* coef,
+                          float* dT);
+
+/* ---------------------------------------------------------------- edge tensors (2-layer) --- */
+
+/*
+ * Y[(i,t), :] = a[idx[i,t]] + b[i] for all edges (first layer of a two-layer EdgeConv,
+ * models/dgcnn.py:119 ec1 and :251). Y [P*k, Cp] fp32 or bf16.
+ */
+int fs_edge_build(int device, fs_stream_t stream, const void* table, int dtype, int ld,
+                  const int32_t* idx, int B, int N, int k, int Cp, void* y, int y_dtype);
+
+/* Backward of fs_edge_build: dT[:, Cp:] = sum_t dY ; dT[idx[i,t], :Cp] += dY (atomics). dT f32 zeroed by caller. */
+int fs_edge_build_bwd(int device, fs_stream_t stream, const void* dy, int dy_dtype,
+                      const int32_t* idx, int B, int N, int k, int Cp, float* dT);
+
+/*
+ * Statistics + max/min over k of a materialised edge tensor Z [P*k, Cp] (second layer output):
+ * same outputs as fs_edgeconv_gather with y := z.
+ */
+int fs_edge_reduce(int device, fs_stream_t stream, const void* z, int z_dtype, long long P, int k,
+                   int Cp, const float* gamma, float* sel, uint8_t* arg, float* sy, double* stats);
+
+/*
+ * Backward of (BatchNorm2d + LeakyReLU + max over k) on a materialised edge tensor:
+ *   dZ[(i,t),c] = s*( [arg[i,c]==t]*d[i,c] - dbeta/M - (dgamma/M)*invstd*(z[(i,t),c]-mu) )
+ * written dense, fp32 or bf16.
+ */
+int fs_edge_reduce_bwd(int device, fs_stream_t stream, const void* z, int z_dtype, const float* d,
+                       const uint8_t* arg, long long P, int k, int Cp, const float* coef,
+                       const double* dgb, double count, int train_stats, void* dz, int dz_dtype);
+
+/* ---------------------------------------------------------------- Chamfer ------------------ */
+
+/*
+ * Nearest neighbour of every x_i among y (squared L2, direct differences), per batch element.
+ * Replaces pytorch3d.ops.knn_points(K=1) inside chamfer_distance (losses/chamfer_loss.py:19).
+ *   x [B,N,3], y [B,M,3] contiguous fp32; nn_d2 [B,N], nn_idx [B,N].
+ */
+int fs_nn_points(int device, fs_stream_t stream, const float* x, const float* y, int B, int N,
+                 int M, float* nn_d2, int32_t* nn_idx);
+
+/*
+ * Chamfer gradient: gx_i += w * 2 (x_i - y_nn(i)), gy_nn(i) -= w * 2 (x_i - y_nn(i)) (atomics).
+ * gx / gy must be zero-initialised by the caller (gy nullable). w_ptr: device scalar upstream grad.
+ */
+int fs_chamfer_bwd(int device, fs_stream_t stream, const float* x, const float* y,
+                   const int32_t* nn_idx, int B, int N, int M, float weight, const float* w_ptr,
+                   float* gx, float* gy);
+
+/* ---------------------------------------------------------------- pointops (gather family) - */
+
+/* grouping: out[m,s,:] = in[idx[m,s],:]  (pointops.py:78) and its backward (:94). */
+int fs_grouping_fwd(int device, fs_stream_t stream, int m, int nsample, int c, const float* in,
+                    const int32_t* idx, float* out);
+int fs_grouping_bwd(int device, fs_stream_t stream, int m, int nsample, int c,
+                    const float* grad_out, const int32_t* idx, float* grad_in);
+/* interpolation: out[n,:] = sum_k w[n,k] * in[idx[n,k],:]  (pointops.py:236) and backward (:252). */
+int fs_interpolation_fwd(int device, fs_stream_t stream, int n, int c, int k, const float* in,
+                         const int32_t* idx, const float* weight, float* out);
+int fs_interpolation_bwd(int device, fs_stream_t stream, int n, int c, int k,
+                         const float* grad_out, const int32_t* idx, const float* weight,
+                         float* grad_in);
+/* subtraction: out[n,s,:] = in1[n,:] - in2[idx[n,s],:]  (pointops.py:139) and backward (:155). */
+int fs_subtraction_fwd(int device, fs_stream_t stream, int n, int nsample, int c, const float* in1,
+                       const float* in2, const int32_t* idx, float* out);
+int fs_subtraction_bwd(int device, fs_stream_t stream, int n, int nsample, int c,
+                       const int32_t* idx, const float* grad_out, float* grad_in1, float* grad_in2);
+/* aggregation: out[n,c] = sum_s (in[idx[n,s],c] + pos[n,s,c]) * w[n,s,c % w_c]  (pointops.py:174, :192). */
+int fs_aggregation_fwd(int device, fs_stream_t stream, int n, int nsample, int c, int w_c,
+                       const float* in, const float* pos, const float* weight, const int32_t* idx,
+                       float* out);
+int fs_aggregation_bwd(int device, fs_stream_t stream, int n, int nsample, int c, int w_c,
+                       const float* in, const float* pos, const float* weight, const int32_t* idx,
+                       const float* grad_out, float* grad_in, float* grad_pos, float* grad_weight);
+
+/* ---------------------------------------------------------------- optimiser ---------------- */
+
+/*
+ * Fused Adam step over a flat parameter buffer (torch.optim.Adam semantics with L2 weight decay,
+ * model_trainer.py:57). `grad_scale` multiplies the gradient (1/world_size averaging); `step` is the 1-based step count. `dyn_step_lr` (nullable) is a device
+ * array [step, lr] that overrides the host values, so a captured CUDA graph can be replayed.
+ */
+int fs_adam_step(int device, fs_stream_t stream, float* param, const float* grad, float* exp_avg,
+                 float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int step, float grad_scale, const float* dyn_step_lr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FISSURE_B200_H */
