@@ -92,13 +92,30 @@ def _ptr(x):
     return x
 
 
+# kernels launched per entry point (for bench.py's gpu_launches claim)
+_LAUNCHES = {"fs_knn_feat": 2}
+launch_count = 0          # kernels of this library launched so far in this process
+timed = {}                # name -> list of (start_event, end_event); filled only for names in `time_calls`
+time_calls = set()
+
+
 def call(name, ref, *args):
     """Invoke fs_<name>(device, stream, *args) on the device / current stream of tensor `ref`."""
+    global launch_count
     lib = load()
     if not ref.is_cuda:
         raise RuntimeError("fissure_b200.%s needs CUDA tensors; there is no CPU path" % name)
     dev = ref.device.index
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    rc = getattr(lib, name)(dev, stream, *[_ptr(a) for a in args])
+    stream = torch.cuda.current_stream(dev)
+    timing = name in time_calls
+    if timing:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+    rc = getattr(lib, name)(dev, stream.cuda_stream, *[_ptr(a) for a in args])
     if rc != 0:
         raise RuntimeError("%s failed: %s (code %d)" % (name, error_string(rc), rc))
+    launch_count += _LAUNCHES.get(name, 1)
+    if timing:
+        e1.record(stream)
+        timed.setdefault(name, []).append((e0, e1))

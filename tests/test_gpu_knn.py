@@ -1,0 +1,105 @@
+"""kNN graph build: CUDA kernels vs the oracle / reference goldens (bit-exact sets except tie rows)."""
+import pytest
+import torch
+
+from fissure_segmentation_b200 import ops, synth
+from fissure_segmentation_b200.knn import knn
+from fissure_segmentation_b200 import dgcnn_opensrc
+from oracle import dgcnn_oracle as O
+from parity import compare_knn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_knn3d_matches_reference_golden(golden, lib):
+    x, _ = synth.make_batch(2, 256, seed=3, jitter=True)
+    for sl in (False, True):
+        idx, d = knn(x.to(DEV), 8, self_loop=sl, return_dist=True)
+        assert idx.dtype == torch.int64 and idx.shape == (2, 256, 8)
+        ref = golden[f"knn3d_idx_sl{int(sl)}"].long()
+        assert torch.equal(idx.cpu().sort(-1)[0], ref.sort(-1)[0])
+        assert torch.equal(idx.cpu(), ref)          # continuous cloud: even the order is identical
+        assert torch.allclose(d.cpu(), golden[f"knn3d_dist_sl{int(sl)}"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(dgcnn_opensrc.knn(x.to(DEV), 8).cpu().sort(-1)[0], golden["knn3d_opensrc_idx"].long().sort(-1)[0])
+
+
+def test_knn_feature_space_matches_reference_golden(golden, lib):
+    gen = torch.Generator().manual_seed(17)
+    feat = torch.randn(2, 64, 256, generator=gen)
+    idx, d = knn(feat.to(DEV), 8, self_loop=True, return_dist=True)
+    assert torch.equal(idx.cpu().sort(-1)[0], golden["knnfeat_idx"].long().sort(-1)[0])
+    assert torch.allclose(d.cpu(), golden["knnfeat_dist"], rtol=1e-4, atol=1e-4)
+    o = dgcnn_opensrc.knn(feat.to(DEV), 8)
+    assert torch.equal(o.cpu().sort(-1)[0], golden["knnfeat_opensrc_idx"].long().sort(-1)[0])
+
+
+@pytest.mark.parametrize("B,N,k,self_loop", [(2, 2048, 20, True), (2, 2048, 20, False), (1, 8192, 40, False),
+                                              (3, 1000, 16, True), (2, 77, 40, False), (1, 300, 100, True)])
+def test_knn3d_continuous_clouds_exact(B, N, k, self_loop, lib):
+    x, _ = synth.make_batch(B, N, seed=100 + N, jitter=True)
+    idx, d = ops.knn_coords(x.to(DEV), k, self_loop=self_loop, return_dist=True)
+    rep = compare_knn(idx, d, x, k, self_loop, O.knn_with_gap)
+    assert rep["mismatch_non_tie_rows"] == 0, rep
+    assert rep["dist_bad"] == 0, rep
+    # size-independent properties: ascending distances, valid and unique indices
+    dc = d.cpu()
+    assert bool((dc[..., 1:] >= dc[..., :-1]).all())
+    ic = idx.cpu().long()
+    assert int(ic.min()) >= 0 and int(ic.max()) < N
+    assert bool((ic.sort(-1)[0][..., 1:] != ic.sort(-1)[0][..., :-1]).all())
+    if self_loop:
+        assert bool((ic[..., 0] == torch.arange(N).view(1, N)).all())
+    else:
+        assert not bool((ic == torch.arange(N).view(1, N, 1)).any())
+
+
+def test_knn3d_lattice_tie_report(golden, lib):
+    """Lattice (integer voxel) clouds: exact distance ties are common; non-tie rows must still match."""
+    x, _ = synth.make_batch(2, 2048, seed=9, jitter=False, augmentation=False)
+    idx, d = ops.knn_coords(x.to(DEV), 20, self_loop=False, return_dist=True)
+    rep = compare_knn(idx, d, x, 20, False, O.knn_with_gap)
+    print("lattice tie report:", rep)
+    assert rep["mismatch_non_tie_rows"] == 0, rep
+    assert rep["mismatch_rows"] <= rep["tie_rows"]
+
+
+@pytest.mark.parametrize("C,N,k", [(64, 2048, 20), (128, 512, 40), (9, 700, 8), (256, 300, 16), (64, 4096, 40)])
+def test_knn_feature_space_exact(C, N, k, lib):
+    gen = torch.Generator().manual_seed(C * 7 + N)
+    feat = torch.randn(2, C, N, generator=gen)
+    feat = feat + 0.5 * torch.randn(2, C, 1, generator=gen)      # common offset, like post-activation features
+    idx, d = ops.knn_any(feat.to(DEV), k, self_loop=True, return_dist=True)
+    rep = compare_knn(idx, None, feat, k, True, O.knn_with_gap)
+    assert rep["mismatch_non_tie_rows"] == 0, rep
+    ref_i, ref_d, _, _ = O.knn_with_gap(feat, k, True)
+    assert torch.allclose(d.cpu().sort(-1)[0], ref_d.sort(-1)[0], rtol=1e-4, atol=2e-4 * float(ref_d.max()))
+
+
+def test_knn_degenerate_inputs(lib):
+    # all points identical (thesis/utils.py:22-23 forwards an all-zero cloud): must not hang or go out of bounds
+    z = torch.zeros(1, 3, 128, device=DEV)
+    idx = ops.knn_coords(z, 20, self_loop=True)
+    assert int(idx.min()) >= 0 and int(idx.max()) < 128
+    # NaN / Inf coordinates
+    x = torch.randn(1, 3, 128, device=DEV)
+    x[0, 0, 5] = float("nan")
+    x[0, 1, 9] = float("inf")
+    idx = ops.knn_coords(x, 8, self_loop=False)
+    torch.cuda.synchronize()
+    assert int(idx.min()) >= 0 and int(idx.max()) < 128
+    # k larger than the cloud raises like torch.topk does in the reference
+    with pytest.raises(RuntimeError):
+        ops.knn_coords(torch.randn(1, 3, 8, device=DEV), 8, self_loop=False)
+    # empty batch
+    assert ops.knn_coords(torch.zeros(0, 3, 16, device=DEV), 4, self_loop=True).shape == (0, 16, 4)
+    # strided input (channels beyond 3 present, non-contiguous view)
+    big = torch.randn(2, 9, 256, device=DEV)
+    a = ops.knn_coords(big, 8, self_loop=True)
+    b = ops.knn_coords(big[:, :3].contiguous(), 8, self_loop=True)
+    assert torch.equal(a, b)
+
+
+def test_no_cpu_fallback(lib):
+    with pytest.raises(RuntimeError):
+        ops.knn_coords(torch.randn(1, 3, 64), 4)
