@@ -33,7 +33,7 @@ def parse_header(path=HEADER):
         text = f.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     protos = {}
-    for m in re.finditer(r"(const char\*|int)\s+(fs_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"(const char\*|int|size_t)\s+(fs_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         arglist = []
         args = " ".join(args.split())
@@ -45,7 +45,8 @@ def parse_header(path=HEADER):
                 else:
                     ty, nm = a.rsplit(" ", 1)
                     arglist.append((_CTYPES[ty.replace("const ", "").strip()], nm))
-        protos[name] = (ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int, arglist)
+        restype = {"int": ctypes.c_int, "size_t": ctypes.c_size_t}.get(ret, ctypes.c_char_p)
+        protos[name] = (restype, arglist)
     return protos
 
 

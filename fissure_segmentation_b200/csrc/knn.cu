@@ -158,8 +158,15 @@ constexpr int KF_TILE_Q = KNN_WARPS * KF_QPW;  // 32 queries per CTA
 template <int KPL>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_feat_kernel(const float* __restrict__ x, int ldx, int N, int C, int k, int self_loop, int diag_zero,
-                int tc, const float* __restrict__ sqnorm, int32_t* __restrict__ idx, float* __restrict__ dist2) {
+                int tc, const float* __restrict__ sqnorm, int32_t* __restrict__ idx, float* __restrict__ dist2,
+                const uint8_t* __restrict__ redo) {
     extern __shared__ float smem[];
+    if (redo) {
+        // masked mode (after the tensor-core path): only rows without certificate are recomputed
+        const int q = blockIdx.x * KF_TILE_Q + (threadIdx.x & 31);
+        const bool mine = (threadIdx.x < 32) && q < N && redo[(long long)blockIdx.y * N + q];
+        if (!__syncthreads_or(mine)) return;
+    }
     const int tcp = tc + 1;                       // padded candidate stride (bank-conflict-free staging)
     float* sq = smem;                             // [C][KF_TILE_Q] query tile, channel-major
     float* sc = sq + C * KF_TILE_Q;               // [C][tcp] candidate chunk, channel-major
@@ -230,7 +237,7 @@ knn_feat_kernel(const float* __restrict__ x, int ldx, int N, int C, int k, int s
 #pragma unroll
     for (int u = 0; u < KF_QPW; ++u) {
         const int q = q0 + warp * KF_QPW + u;
-        if (q < N) {
+        if (q < N && (!redo || redo[cloud0 + q])) {
             sel[u].finish();
             const long long row = (cloud0 + q) * k;
             sel[u].store(self_loop ? 0 : 1, idx + row, dist2 ? dist2 + row : nullptr, 0, 0, INFINITY);
@@ -252,10 +259,11 @@ int set_smem(K kernel, size_t bytes) {
 extern "C" int fs_knn3d(int device, fs_stream_t stream_, const float* coords, long long batch_stride,
                         long long chan_stride, long long point_stride, int B, int N, int k, int self_loop,
                         int diag_zero, int32_t* idx, float* dist2) {
-    if (!coords || !idx || B < 0 || N < 0 || k <= 0) return FS_ERR_BAD_ARG;
+    if (B < 0 || N < 0 || k <= 0) return FS_ERR_BAD_ARG;
+    if (B == 0) return FS_OK;  // empty batch: nothing to do, pointers may be null
+    if (!coords || !idx) return FS_ERR_BAD_ARG;
     const int kk = k + (self_loop ? 0 : 1);
     if (kk > N || kk > FS_MAX_K + 1) return FS_ERR_BAD_ARG;
-    if (B == 0 || N == 0) return FS_OK;
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int chunk = N < KNN3D_MAX_CHUNK ? ((N + 31) / 32) * 32 : KNN3D_MAX_CHUNK;
@@ -295,18 +303,10 @@ extern "C" int fs_knnquery(int device, fs_stream_t stream_, int m, int nsample, 
     return FS_OK;
 }
 
-extern "C" int fs_knn_feat(int device, fs_stream_t stream_, const float* x, int ldx, int B, int N, int C, int k,
-                           int self_loop, int diag_zero, int32_t* idx, float* dist2, float* sqnorm_ws) {
-    if (!x || !idx || !sqnorm_ws || B < 0 || N < 0 || C <= 0 || k <= 0 || ldx < C) return FS_ERR_BAD_ARG;
+// Shared launcher of the exact kernel; `redo` (nullable) restricts it to flagged rows.
+static int launch_knn_feat(cudaStream_t stream, const float* x, int ldx, int B, int N, int C, int k, int self_loop,
+                           int diag_zero, int32_t* idx, float* dist2, const float* sqnorm, const uint8_t* redo) {
     const int kk = k + (self_loop ? 0 : 1);
-    if (kk > N || kk > FS_MAX_K + 1) return FS_ERR_BAD_ARG;
-    if (C > 1024) return FS_ERR_UNSUPPORTED;
-    if (B == 0 || N == 0) return FS_OK;
-    FS_ENTER(device);
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const long long P = (long long)B * N;
-    row_sqnorm_kernel<<<fs_div_up(P, 8), 256, 0, stream>>>(x, ldx, P, C, sqnorm_ws);
-    FS_RETURN_IF_LAUNCH_FAILED();
     // candidate chunk: keep the staged chunk near 64 KB
     int tc = (16384 / C) / 32 * 32;
     if (tc < 32) tc = 32;
@@ -320,10 +320,35 @@ extern "C" int fs_knn_feat(int device, fs_stream_t stream_, const float* x, int 
         int e = set_smem(knn_feat_kernel<KPL>, smem);                                              \
         if (e) return e;                                                                           \
         knn_feat_kernel<KPL><<<grid, KNN_THREADS, smem, stream>>>(x, ldx, N, C, k, self_loop,      \
-                                                                  diag_zero, tc, sqnorm_ws, idx, dist2); \
+                                                                  diag_zero, tc, sqnorm, idx, dist2, redo); \
     } while (0)
     if (kk <= 32) LAUNCHF(1); else if (kk <= 64) LAUNCHF(2); else LAUNCHF(4);
 #undef LAUNCHF
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
+}
+
+// Used by knn_tc.cu.
+void fs_row_sqnorm(cudaStream_t stream, const float* x, int ldx, long long P, int C, float* out) {
+    row_sqnorm_kernel<<<fs_div_up(P, 8), 256, 0, stream>>>(x, ldx, P, C, out);
+}
+int fs_knn_feat_masked(cudaStream_t stream, const float* x, int ldx, int B, int N, int C, int k, int self_loop,
+                       int diag_zero, int32_t* idx, float* dist2, const float* sqnorm, const uint8_t* redo) {
+    return launch_knn_feat(stream, x, ldx, B, N, C, k, self_loop, diag_zero, idx, dist2, sqnorm, redo);
+}
+
+extern "C" int fs_knn_feat(int device, fs_stream_t stream_, const float* x, int ldx, int B, int N, int C, int k,
+                           int self_loop, int diag_zero, int32_t* idx, float* dist2, float* sqnorm_ws) {
+    if (B < 0 || N < 0 || C <= 0 || k <= 0 || ldx < C) return FS_ERR_BAD_ARG;
+    if (B == 0) return FS_OK;
+    if (!x || !idx || !sqnorm_ws) return FS_ERR_BAD_ARG;
+    const int kk = k + (self_loop ? 0 : 1);
+    if (kk > N || kk > FS_MAX_K + 1) return FS_ERR_BAD_ARG;
+    if (C > 1024) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long P = (long long)B * N;
+    row_sqnorm_kernel<<<fs_div_up(P, 8), 256, 0, stream>>>(x, ldx, P, C, sqnorm_ws);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return launch_knn_feat(stream, x, ldx, B, N, C, k, self_loop, diag_zero, idx, dist2, sqnorm_ws, nullptr);
 }

@@ -49,10 +49,7 @@ def edgeconv_stage(x_pm, B, N, k, conv, graph, cdt):
     C = x_pm.shape[1]
     w = conv2d.weight.view(conv2d.out_channels, 2 * C)
     w_cat = torch.cat([w[:, :C], w[:, C:] - w[:, :C]], dim=0)
-    if C <= 16:
-        table = (x_pm.float() @ w_cat.float().t()).to(cdt)
-    else:
-        table = x_pm.to(cdt) @ w_cat.to(cdt).t()
+    table = x_pm.float() @ w_cat.float().t()      # fp32 table in every mode (see dgcnn.EdgeConv.forward_pm)
     return ops.edgeconv_fused(table, bn.weight, bn.bias, graph, bn.running_mean, bn.running_var,
                               bn.num_batches_tracked, bn.training, eps=bn.eps, momentum=bn.momentum)
 
@@ -106,7 +103,7 @@ class DGCNN(nn.Module):
     def forward(self, x):
         B, _, N = x.shape
         with torch.autocast("cuda", enabled=False):
-            feats = self.encode(x)                                                  # (B*N, 512)
+            feats = self.encode(x).to(_compute_dtype(self.precision))               # (B*N, 512)
             w5 = self.conv5[0].weight.view(self.conv5[0].out_channels, 512)
             e = feats @ w5.to(feats.dtype).t()
             bn = self.bn5

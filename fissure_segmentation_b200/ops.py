@@ -10,6 +10,7 @@ from . import _lib
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+USE_TENSOR_CORE_KNN = True   # feature-space kNN (C == 64): tcgen05 candidates + exact re-rank
 
 
 class KnnGraph:
@@ -73,6 +74,17 @@ def knn_features(feat, B, N, k, self_loop=False, diag_zero=True, return_dist=Fal
     C = feat.shape[1]
     idx = torch.empty(B, N, k, dtype=torch.int32, device=feat.device)
     dist = torch.empty(B, N, k, dtype=torch.float32, device=feat.device) if return_dist else None
+    if B == 0:
+        return (idx, dist) if return_dist else idx
+    lib = _lib.load()
+    if (USE_TENSOR_CORE_KNN and feat.stride(0) % 4 == 0 and feat.data_ptr() % 16 == 0
+            and lib.fs_knn_feat_tc_supported(B, N, C, k, int(self_loop))):
+        # tcgen05 candidate search + exact FP32 re-rank (same result as the exact kernel)
+        nbytes = lib.fs_knn_feat_tc_workspace_bytes(B, N, C, k)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device)
+        _lib.call("fs_knn_feat_tc", feat, feat, feat.stride(0), B, N, C, k, int(self_loop), int(diag_zero), idx, dist,
+                  ws, nbytes)
+        return (idx, dist) if return_dist else idx
     ws = torch.empty(B * N, dtype=torch.float32, device=feat.device)
     _lib.call("fs_knn_feat", feat, feat, feat.stride(0), B, N, C, k, int(self_loop), int(diag_zero), idx, dist, ws)
     return (idx, dist) if return_dist else idx

@@ -71,6 +71,21 @@ int fs_knn_feat(int device, fs_stream_t stream, const float* x, int ldx, int B, 
                 int self_loop, int diag_zero, int32_t* idx, float* dist2, float* sqnorm_ws);
 
 /*
+ * Same contract as fs_knn_feat for C == 64 features, on the 5th-generation tensor cores: the
+ * -2 X X^T contraction runs as tcgen05.mma on TMA-staged bf16 hi/lo-split tiles (accumulators in TMEM),
+ * the epilogue keeps 32 candidates per query, and an exact FP32 re-rank (identical arithmetic to
+ * fs_knn_feat) selects the k nearest. Rows whose candidate set cannot be certified complete are
+ * recomputed by the exact kernel, so the result equals fs_knn_feat's.
+ *   workspace        >= fs_knn_feat_tc_workspace_bytes(B, N, C, k) bytes, 256-byte aligned
+ * fs_knn_feat_tc_supported returns 1 when the shape is handled (C == 64, k + 5 <= 32, N <= 8192).
+ */
+size_t fs_knn_feat_tc_workspace_bytes(int B, int N, int C, int k);
+int fs_knn_feat_tc_supported(int B, int N, int C, int k, int self_loop);
+int fs_knn_feat_tc(int device, fs_stream_t stream, const float* x, int ldx, int B, int N, int C, int k,
+                   int self_loop, int diag_zero, int32_t* idx, float* dist2, void* workspace,
+                   size_t workspace_bytes);
+
+/*
  * Offset-segmented kNN of `new_xyz` in `xyz` (direct squared differences).
  * Replaces pointops_cuda.knnquery_cuda at models/pointtransformer/pointops.py:59.
  *   xyz [n,3], new_xyz [m,3], offset [b], new_offset [b]: cumulative int32 segment ends

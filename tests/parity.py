@@ -8,14 +8,14 @@ def compare_knn(idx_gpu, dist_gpu, x_bcn_cpu, k, self_loop, oracle_knn_with_gap)
     """Compare a CUDA kNN result with the oracle row by row.
 
     A row is a *tie row* when the oracle's gap between the last kept and the first rejected neighbour
-    is within 4 eps (|x_i|^2 + |x_j|^2) — there the reference's own fp32 answer is arbitrary. Non-tie
+    is within 16 eps (|x_i|^2 + max_j |x_j|^2) — there the reference's own fp32 answer is arbitrary. Non-tie
     rows must have exactly the oracle's index SET; sorted distances must agree to rtol 1e-5 (abs 1e-6
     of the squared-norm scale). Returns a report dict.
     """
     ref_i, ref_d, next_d, sq = oracle_knn_with_gap(x_bcn_cpu, k, self_loop)
     gi = idx_gpu.cpu().long()
     B, N, _ = gi.shape
-    scale = 4 * EPS32 * (sq.unsqueeze(-1) + sq.max(dim=1, keepdim=True)[0].unsqueeze(-1))     # (B, N, 1) upper bound
+    scale = 16 * EPS32 * (sq.unsqueeze(-1) + sq.max(dim=1, keepdim=True)[0].unsqueeze(-1))     # (B, N, 1) upper bound
     gap = (next_d - ref_d[..., -1]).unsqueeze(-1)
     # also ties inside the kept list do not matter for sets; only the boundary does
     tie_row = (gap <= scale).squeeze(-1)

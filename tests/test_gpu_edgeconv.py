@@ -79,13 +79,14 @@ def test_single_layer_edgeconv_vs_oracle(lib, C, Cp, N, k, training):
 
 
 def test_edgeconv_bf16_tables_within_stated_tolerance(lib):
-    """bf16 tables vs the fp32 oracle: rtol 2e-2 / atol 2e-2 on outputs, cosine >= 0.999 on gradients."""
-    B, C, Cp, N, k = 2, 64, 64, 1024, 20
+    """bf16 mode (bf16 edge tensors / second-layer GEMM of a two-layer EdgeConv; the per-point tables stay
+    fp32) vs the fp32 oracle: rtol 3e-2 / atol 3e-2 on outputs, cosine >= 0.999 on gradients."""
+    B, C, Cp, N, k = 2, 64, 128, 1024, 20
     gen = torch.Generator().manual_seed(5)
     x = torch.randn(B, C, N, generator=gen)
     graph = O.knn(x, k, self_loop=True)
-    p = O.make_params(_shapes(2 * C, [Cp]), 43)
-    ec = fs.EdgeConv(C, [Cp], k).to(DEV)
+    p = O.make_params(_shapes(2 * C, [64, Cp]), 43)
+    ec = fs.EdgeConv(C, [64, Cp], k).to(DEV)
     ec.load_state_dict(p)
     ec.precision = "bf16"
     ec.train()
@@ -94,8 +95,8 @@ def test_edgeconv_bf16_tables_within_stated_tolerance(lib):
     xo = x.clone().requires_grad_(True)
     po = {"ec." + n: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in n else v)
           for n, v in p.items()}
-    ref = O.edgeconv(xo, po, "ec", 1, k, graph, False, True, None)
-    assert_close(out, ref, 2e-2, 2e-2, "bf16 forward")
+    ref = O.edgeconv(xo, po, "ec", 2, k, graph, False, True, None)
+    assert_close(out, ref, 3e-2, 3e-2, "bf16 forward")
     gout = torch.randn(ref.shape, generator=gen)
     out.backward(gout.to(DEV))
     ref.backward(gout)
