@@ -336,6 +336,12 @@ int fs_knn_feat_masked(cudaStream_t stream, const float* x, int ldx, int B, int 
                        int diag_zero, int32_t* idx, float* dist2, const float* sqnorm, const uint8_t* redo) {
     return launch_knn_feat(stream, x, ldx, B, N, C, k, self_loop, diag_zero, idx, dist2, sqnorm, redo);
 }
+int fs_knn_feat_exact(cudaStream_t stream, const float* x, int ldx, int B, int N, int C, int k, int self_loop,
+                      int diag_zero, int32_t* idx, float* dist2, float* sqnorm_ws) {
+    row_sqnorm_kernel<<<fs_div_up((long long)B * N, 8), 256, 0, stream>>>(x, ldx, (long long)B * N, C, sqnorm_ws);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return launch_knn_feat(stream, x, ldx, B, N, C, k, self_loop, diag_zero, idx, dist2, sqnorm_ws, nullptr);
+}
 
 extern "C" int fs_knn_feat(int device, fs_stream_t stream_, const float* x, int ldx, int B, int N, int C, int k,
                            int self_loop, int diag_zero, int32_t* idx, float* dist2, float* sqnorm_ws) {

@@ -4,35 +4,54 @@
 // (utils/general_utils.py:43-53 + :315-327, called from models/dgcnn.py:26 on 64-channel features).
 // Here the -2 X X^T contraction runs on tcgen05.mma and the N x N scores never leave the SM:
 //
-//   1. prep      : per cloud, centre the features, split every value into bf16 hi + lo and write two
-//                  operand tables A', B' (P x 256 bf16) such that one K = 208 tensor-core product gives
-//                      A'_i . B'_j = |x_i|^2 + |x_j|^2 - 2 x_i.x_j       (error ~ 2^-16 |x_i||x_j|)
-//                  (hi*hi + lo*hi + hi*lo in K = 192, the squared norms ride in 16 extra K columns).
-//   2. candidates: one CTA per (cloud, 128 queries). TMA stages 128-row operand tiles (128B swizzle),
-//                  one elected thread issues tcgen05.mma (M = 128 queries, N = 128 candidates) into a
-//                  double-buffered TMEM accumulator, and four epilogue warps read the scores with
-//                  tcgen05.ld — one query row per thread — keeping the KP smallest (distance,index)
-//                  keys of their row in registers (branch-free compare-exchange chain).
-//   3. re-rank   : exact FP32 distances in the reference's own arithmetic for the KP candidates, warp
-//                  bitonic top-k, and a per-row certificate that no non-candidate can belong to the
-//                  top-k; rows without certificate are redone by the exact SIMT kernel (knn.cu).
+//   1. prep     : per cloud, centre the features, split every value into bf16 hi + lo and write two
+//                 operand tables A', B' (P x 256 bf16) such that one K = 208 tensor-core product gives
+//                     A'_i . B'_j = |x_i|^2 + |x_j|^2 - 2 x_i.x_j        (error ~ 2^-15 (|x_i|^2+|x_j|^2))
+//                 (hi*hi + lo*hi + hi*lo in K = 192; the squared norms ride in 16 extra K columns).
+//   2. select   : one CTA per (cloud, 256 queries). TMA stages 128B-swizzled operand tiles, one elected
+//                 thread issues tcgen05.mma (M = 128 queries x N = 64 candidates, two query tiles share
+//                 every candidate tile) into double-buffered TMEM accumulators, four epilogue warps read
+//                 the scores with tcgen05.ld, one query row per TMEM lane. The distance matrix is swept
+//                 twice: sweep 1 keeps, per row, the minimum of each of 32 interleaved column classes
+//                 (32 FMNMX per 32 scores) — the kk-th smallest class minimum is an upper bound tau of the
+//                 kk-th smallest distance; sweep 2 stores every (index, distance) with distance <= tau +
+//                 2 err (about 1.5 kk entries per row). No sorted list, no dependent chains: MMA-bound.
+//   3. finalize : one warp per query sorts its <= 64 survivors by approximate distance. Entries further
+//                 than 2 err from the kk-th are decided by the approximation alone; the few within 2 err
+//                 are re-evaluated exactly in the reference's FP32 arithmetic (same code as knn.cu), so
+//                 the neighbour SET equals the exact kernel's. Rows whose survivor list overflowed are
+//                 recomputed by the exact SIMT kernel.
 #include <cuda.h>
 
 #include "warp_select.cuh"
 
 namespace {
 
-constexpr int TC_M = 128;          // queries per CTA  (UMMA M, TMEM lanes)
-constexpr int TC_N = 128;          // candidates per tile (UMMA N, TMEM columns per accumulator)
+constexpr int TC_M = 128;          // queries per query tile (UMMA M, TMEM lanes)
+constexpr int TC_QT = 2;           // query tiles per CTA (share each candidate tile)
+constexpr int TC_NB = 64;          // candidates per tile (UMMA N)
 constexpr int TC_C = 64;           // feature channels handled by this path
 constexpr int TC_KROW = 256;       // bf16 elements per operand row: 3 x 64 data + 64 (16 used) extras
 constexpr int TC_BOXES = 4;        // TMA boxes (64 bf16 = 128 B wide) per operand row
-constexpr int TC_BOX_BYTES = TC_M * 128;            // one 128-row x 128-B box in shared memory
-constexpr int TC_TILE_BYTES = TC_BOXES * TC_BOX_BYTES;
+constexpr int TC_ABOX_BYTES = TC_M * 128;
+constexpr int TC_ATILE_BYTES = TC_BOXES * TC_ABOX_BYTES;     // 64 KB
+constexpr int TC_BBOX_BYTES = TC_NB * 128;
+constexpr int TC_BTILE_BYTES = TC_BOXES * TC_BBOX_BYTES;     // 32 KB
 constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 192;    // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
-constexpr int TC_KP = 32;          // candidates kept per query
-constexpr int TC_SMEM_BYTES = TC_TILE_BYTES * (1 + TC_STAGES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_EPI_WARPS = 4 * TC_QT;   // one epilogue warpgroup per query tile (TMEM lane = query row)
+constexpr int TC_WARP_TMA = TC_EPI_WARPS;
+constexpr int TC_WARP_MMA = TC_EPI_WARPS + 1;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_STAGE_BYTES = 32 * 32 * 4;  // per-warp staging of one 32 x 32 score block (sweep 2)
+constexpr int TC_CAP = 64;         // survivor slots per query
+constexpr int TC_NCLS = 32;        // interleaved column classes of sweep 1
+constexpr int TC_MAX_KK = 24;      // kk-th smallest of 32 class minima stays near rank 1.6 kk up to here
+constexpr int TC_TMEM_COLS = TC_STAGES * TC_QT * TC_NB;      // 256
+constexpr int TC_SMEM_BYTES = TC_QT * TC_ATILE_BYTES + TC_STAGES * TC_BTILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                              TC_EPI_WARPS * TC_STAGE_BYTES;
+
+constexpr float TC_ERR_CENTRED = 6.2e-5f;   // 2^-14: bound of the bf16 hi/lo product error, per (|xi|^2+|xj|^2)
+constexpr float TC_ERR_RAW = 1.0e-6f;       // rounding of the exact FP32 expansion form, per raw squared norm
 
 // ----------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,8 +98,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128.
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N = 64, M = 128.
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_NB >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
     asm volatile(
@@ -93,27 +112,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Candidate tiles are visited nearest-first around the query tile (qt, qt+1, qt-1, qt+2, ...): with
-// spatially sorted points the selection threshold is tight after the first tile.
-__device__ __forceinline__ int tile_at(int t, int qt, int T) {
-    const int L = qt, R = T - 1 - qt;
-    const int m = L < R ? L : R;
-    if (t <= 2 * m) return qt + ((t & 1) ? ((t + 1) >> 1) : -(t >> 1));
-    return R > L ? qt + t - m : qt - (t - m);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // ----------------------------------------------------------------------------------------------- prep
@@ -137,11 +150,12 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& h, __nv_bfloat16&
     l2 = __float2bfloat16_rn(r1 - __bfloat162float(l));
 }
 
-// One warp per point: lane handles channels 2*lane, 2*lane+1.
+// One warp per point: lane handles channels 2*lane, 2*lane+1 of the operand rows; the raw squared norm is
+// summed exactly like row_sqnorm_kernel (knn.cu) so the exact re-evaluation matches the exact kernel bit for bit.
 __global__ void __launch_bounds__(256)
 tc_split_kernel(const float* __restrict__ x, int ldx, long long P, int N, const float* __restrict__ sums,
                 __nv_bfloat16* __restrict__ A, __nv_bfloat16* __restrict__ Bm, float* __restrict__ cnorm,
-                int* __restrict__ cnorm_max_bits) {
+                float* __restrict__ sqnorm, int* __restrict__ norm_max_bits /* [B][2]: centred, raw */) {
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= P) return;
     const int lane = threadIdx.x & 31;
@@ -155,7 +169,9 @@ tc_split_kernel(const float* __restrict__ x, int ldx, long long P, int N, const 
     split3(v1, h1, l1, t1);
     // the norm that rides in the GEMM is the norm of the values the GEMM actually multiplies (hi + lo)
     const float e0 = __bfloat162float(h0) + __bfloat162float(l0), e1 = __bfloat162float(h1) + __bfloat162float(l1);
-    float nrm = fs_warp_sum(e0 * e0 + e1 * e1);
+    const float nrm = fs_warp_sum(e0 * e0 + e1 * e1);
+    const float ra = __ldg(x + row * ldx + lane), rb = __ldg(x + row * ldx + lane + 32);
+    const float raw = fs_warp_sum(__fadd_rn(__fadd_rn(0.f, __fmul_rn(ra, ra)), __fmul_rn(rb, rb)));
     __nv_bfloat162* Ar = reinterpret_cast<__nv_bfloat162*>(A + row * TC_KROW);
     __nv_bfloat162* Br = reinterpret_cast<__nv_bfloat162*>(Bm + row * TC_KROW);
     const __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
@@ -175,29 +191,61 @@ tc_split_kernel(const float* __restrict__ x, int ldx, long long P, int N, const 
     Br[96 + lane] = __halves2bfloat162(eb0, eb1);
     if (lane == 0) {
         cnorm[row] = nrm;
-        atomicMax(cnorm_max_bits + b, __float_as_int(nrm));
+        sqnorm[row] = raw;
+        atomicMax(norm_max_bits + 2 * b, __float_as_int(nrm));
+        atomicMax(norm_max_bits + 2 * b + 1, __float_as_int(raw));
     }
 }
 
-// ----------------------------------------------------------------------------------------------- candidates
+__device__ __forceinline__ float tc_row_err(float cn, float cmax, float rn, float rmax) {
+    return TC_ERR_CENTRED * (cn + cmax) + TC_ERR_RAW * (rn + rmax) + 1e-30f;
+}
+
+// Ascending bitonic sorting network on 32 registers; every index is a compile-time constant.
+template <int SIZE, int STRIDE>
+__device__ __forceinline__ void bitonic_layer32(float (&g)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        constexpr int dummy = 0; (void)dummy;
+        const int p = i ^ STRIDE;
+        if (p > i) {
+            const bool up = (i & SIZE) == 0;
+            const float lo = fminf(g[i], g[p]), hi = fmaxf(g[i], g[p]);
+            g[i] = up ? lo : hi;
+            g[p] = up ? hi : lo;
+        }
+    }
+}
+__device__ __forceinline__ void bitonic_sort32(float (&g)[32]) {
+    bitonic_layer32<2, 1>(g);
+    bitonic_layer32<4, 2>(g); bitonic_layer32<4, 1>(g);
+    bitonic_layer32<8, 4>(g); bitonic_layer32<8, 2>(g); bitonic_layer32<8, 1>(g);
+    bitonic_layer32<16, 8>(g); bitonic_layer32<16, 4>(g); bitonic_layer32<16, 2>(g); bitonic_layer32<16, 1>(g);
+    bitonic_layer32<32, 16>(g); bitonic_layer32<32, 8>(g); bitonic_layer32<32, 4>(g); bitonic_layer32<32, 2>(g);
+    bitonic_layer32<32, 1>(g);
+}
+
+// ----------------------------------------------------------------------------------------------- select
 __global__ void __launch_bounds__(TC_THREADS, 1)
-knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         int N, int idx_bits, int32_t* __restrict__ cand /* [P, TC_KP] packed keys */) {
+knn_tc_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int N, int kk,
+                     int diag_zero, const float* __restrict__ cnorm, const float* __restrict__ sqnorm,
+                     const int* __restrict__ norm_max_bits, int32_t* __restrict__ cand_j, float* __restrict__ cand_d,
+                     int32_t* __restrict__ cand_n) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + TC_TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_TILE_BYTES * (1 + TC_STAGES));
+    uint8_t* smem_b = smem + TC_QT * TC_ATILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + TC_STAGES * TC_BTILE_BYTES);
     // bars: 0 a_full | 1,2 b_full | 3,4 b_empty | 5,6 acc_full | 7,8 acc_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* stage_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int T = (N + TC_N - 1) / TC_N;          // candidate tiles per cloud
-    const int qt = blockIdx.x;                     // query tile of this CTA
+    const int T = (N + TC_NB - 1) / TC_NB;        // candidate tiles per sweep
     const int b = blockIdx.y;
     const long long cloud0 = (long long)b * N;
-    const int q_row0 = qt * TC_M;
+    const int q_row0 = blockIdx.x * (TC_QT * TC_M);
 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(bars + 0), 1);
@@ -205,12 +253,12 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             mbar_init(smem_u32(bars + 1 + s), 1);
             mbar_init(smem_u32(bars + 3 + s), 1);
             mbar_init(smem_u32(bars + 5 + s), 1);
-            mbar_init(smem_u32(bars + 7 + s), 4);
+            mbar_init(smem_u32(bars + 7 + s), TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    if (warp == TC_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -218,86 +266,120 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == TC_WARP_TMA) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-            mbar_expect_tx(smem_u32(bars + 0), TC_TILE_BYTES);
-            for (int bx = 0; bx < TC_BOXES; ++bx)
-                tma_load_2d(smem_u32(smem_a + bx * TC_BOX_BYTES), &map_a, smem_u32(bars + 0), bx * 64,
-                            (int)(cloud0 + q_row0));
-            for (int t = 0; t < T; ++t) {
-                const int s = t % TC_STAGES;
-                const uint32_t ph = (t / TC_STAGES) & 1;
-                mbar_wait(smem_u32(bars + 3 + s), ph ^ 1);
-                mbar_expect_tx(smem_u32(bars + 1 + s), TC_TILE_BYTES);
-                const int row = (int)(cloud0 + tile_at(t, qt, T) * TC_N);
+            mbar_expect_tx(smem_u32(bars + 0), TC_QT * TC_ATILE_BYTES);
+            for (int u = 0; u < TC_QT; ++u)
                 for (int bx = 0; bx < TC_BOXES; ++bx)
-                    tma_load_2d(smem_u32(smem_b + s * TC_TILE_BYTES + bx * TC_BOX_BYTES), &map_b, smem_u32(bars + 1 + s),
+                    tma_load_2d(smem_u32(smem_a + u * TC_ATILE_BYTES + bx * TC_ABOX_BYTES), &map_a, smem_u32(bars + 0),
+                                bx * 64, (int)(cloud0 + q_row0 + u * TC_M));
+            for (int it = 0; it < 2 * T; ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (it / TC_STAGES) & 1;
+                mbar_wait(smem_u32(bars + 3 + s), ph ^ 1);
+                mbar_expect_tx(smem_u32(bars + 1 + s), TC_BTILE_BYTES);
+                const int row = (int)(cloud0 + (it % T) * TC_NB);
+                for (int bx = 0; bx < TC_BOXES; ++bx)
+                    tma_load_2d(smem_u32(smem_b + s * TC_BTILE_BYTES + bx * TC_BBOX_BYTES), &map_b, smem_u32(bars + 1 + s),
                                 bx * 64, row);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer =====================
         mbar_wait(smem_u32(bars + 0), 0);
-        for (int t = 0; t < T; ++t) {
-            const int s = t % TC_STAGES;
-            const uint32_t ph = (t / TC_STAGES) & 1;
+        for (int it = 0; it < 2 * T; ++it) {
+            const int s = it % TC_STAGES;
+            const uint32_t ph = (it / TC_STAGES) & 1;
             mbar_wait(smem_u32(bars + 1 + s), ph);          // operands landed
-            mbar_wait(smem_u32(bars + 7 + s), ph ^ 1);      // accumulator buffer drained by the epilogue
+            mbar_wait(smem_u32(bars + 7 + s), ph ^ 1);      // accumulators of this stage drained by the epilogue
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t acc = tmem_base + s * TC_N;
-                uint32_t accumulate = 0;
-                for (int bx = 0; bx < TC_BOXES; ++bx) {
-                    const int nk = bx < 3 ? 4 : 1;          // extras box: only its first 16 K columns are non-zero
-                    for (int kk = 0; kk < nk; ++kk) {
-                        const uint64_t da = umma_desc_sw128(smem_u32(smem_a + bx * TC_BOX_BYTES) + kk * 32);
-                        const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * TC_TILE_BYTES + bx * TC_BOX_BYTES) + kk * 32);
-                        umma_bf16(acc, da, db, accumulate);
-                        accumulate = 1;
+                for (int u = 0; u < TC_QT; ++u) {
+                    const uint32_t acc = tmem_base + (s * TC_QT + u) * TC_NB;
+                    uint32_t accumulate = 0;
+                    for (int bx = 0; bx < TC_BOXES; ++bx) {
+                        const int nk = bx < 3 ? 4 : 1;      // extras box: only its first 16 K columns are non-zero
+                        for (int kq = 0; kq < nk; ++kq) {
+                            const uint64_t da = umma_desc_sw128(smem_u32(smem_a + u * TC_ATILE_BYTES + bx * TC_ABOX_BYTES) + kq * 32);
+                            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * TC_BTILE_BYTES + bx * TC_BBOX_BYTES) + kq * 32);
+                            umma_bf16(acc, da, db, accumulate);
+                            accumulate = 1;
+                        }
                     }
                 }
                 umma_commit(smem_u32(bars + 3 + s));        // smem stage free once these MMAs retire
-                umma_commit(smem_u32(bars + 5 + s));        // accumulator ready
+                umma_commit(smem_u32(bars + 5 + s));        // accumulators ready
             }
             __syncwarp();
         }
     } else {
-        // ===================== epilogue: one query row per thread =====================
-        int list[TC_KP];
+        // ===================== epilogue: warpgroup u owns query tile u, TMEM lane = query row =====================
+        const int u = warp >> 2;                       // query tile of this warpgroup
+        const int w4 = warp & 3;                       // TMEM lane quarter this warp may access
+        const int qrow = q_row0 + u * TC_M + w4 * 32 + lane;
+        const bool row_ok = qrow < N;
+        float* stage = stage_all + warp * (TC_STAGE_BYTES / 4) + lane * 32;   // this thread's 32 staged scores
+        float gm[TC_NCLS];
 #pragma unroll
-        for (int i = 0; i < TC_KP; ++i) list[i] = 0x7fffffff;
-        const int idx_mask = (1 << idx_bits) - 1;
-        for (int t = 0; t < T; ++t) {
-            const int s = t % TC_STAGES;
-            const uint32_t ph = (t / TC_STAGES) & 1;
-            const int col0 = tile_at(t, qt, T) * TC_N;
+        for (int e = 0; e < TC_NCLS; ++e) gm[e] = INFINITY;
+        float tau = INFINITY;
+        int cnt = 0;
+        const long long out_base = (cloud0 + (row_ok ? qrow : 0)) * TC_CAP;
+        for (int it = 0; it < 2 * T; ++it) {
+            const int s = it % TC_STAGES;
+            const uint32_t ph = (it / TC_STAGES) & 1;
+            const int j0 = (it % T) * TC_NB;
+            if (it == T) {
+                // between the sweeps: tau = kk-th smallest class minimum (+ 2 err); bitonic network in registers
+                bitonic_sort32(gm);
+                float t = -INFINITY;   // sorted ascending: kk-th smallest = max of the first kk (no indexed register access)
+#pragma unroll
+                for (int i = 0; i < TC_NCLS; ++i) t = fmaxf(t, i < kk ? gm[i] : -INFINITY);
+                const float cmax = __int_as_float(__ldg(norm_max_bits + 2 * b)), rmax = __int_as_float(__ldg(norm_max_bits + 2 * b + 1));
+                const int q = row_ok ? qrow : N - 1;
+                tau = t + 2.f * tc_row_err(__ldg(cnorm + cloud0 + q), cmax, __ldg(sqnorm + cloud0 + q), rmax);
+            }
             mbar_wait(smem_u32(bars + 5 + s), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int cb = 0; cb < TC_N / 32; ++cb) {
-                int v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * TC_N + cb * 32), v);
-                const int jbase = col0 + cb * 32;
-                const int nvalid = N - jbase;           // columns >= nvalid belong to the next cloud / padding
-                const int thr_hi = list[TC_KP - 1] | idx_mask;
-                unsigned hits = 0;
+            for (int cb = 0; cb < TC_NB / 32; ++cb) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)((s * TC_QT + u) * TC_NB + cb * 32), v);
+                const int jb = j0 + cb * 32;
+                if (jb + 32 > N) {         // last tile: columns beyond the cloud are padding / the next cloud
 #pragma unroll
-                for (int e = 0; e < 32; ++e) hits |= (v[e] <= thr_hi) ? (1u << e) : 0u;
-                if (nvalid < 32) hits &= nvalid <= 0 ? 0u : ((1u << nvalid) - 1u);
-                unsigned any = __reduce_or_sync(FS_FULL_MASK, hits);
+                    for (int e = 0; e < 32; ++e) v[e] = (jb + e < N) ? v[e] : INFINITY;
+                }
+                if (diag_zero && __any_sync(FS_FULL_MASK, qrow >= jb && qrow < jb + 32)) {
+                    // the reference forces d(i,i) = 0 (general_utils.py:52): the query itself always survives
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    if (any & (1u << e)) {      // warp-uniform: some row of this warp accepts column e
-                        int key = (hits & (1u << e)) ? ((v[e] & ~idx_mask) | (jbase + e)) : 0x7fffffff;
+                    for (int e = 0; e < 32; ++e) v[e] = (jb + e == qrow) ? -FLT_MAX : v[e];
+                }
+                if (it < T) {
 #pragma unroll
-                        for (int i = 0; i < TC_KP; ++i) {
-                            const int lo = min(list[i], key);
-                            key = max(list[i], key);
-                            list[i] = lo;
+                    for (int e = 0; e < 32; ++e) gm[e] = fminf(gm[e], v[e]);
+                } else {
+                    // sweep 2: branch-free hit mask, scores staged in shared memory (16-byte chunks XOR-swizzled by
+                    // lane so the 128-bit stores are conflict-free), then each lane walks its own few hits
+                    unsigned hits = 0;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) hits |= (v[e] <= tau) ? (1u << e) : 0u;
+                    if (!row_ok) hits = 0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<float4*>(stage + ((c ^ (lane & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    while (hits) {
+                        const int e = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const float dv = stage[(((e >> 2) ^ (lane & 7)) << 2) + (e & 3)];
+                        if (cnt < TC_CAP) {
+                            cand_j[out_base + cnt] = jb + e;
+                            cand_d[out_base + cnt] = dv;
                         }
+                        ++cnt;
                     }
                 }
             }
@@ -305,29 +387,25 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(bars + 7 + s));
         }
-        const int q = q_row0 + warp * 32 + lane;
-        if (q < N) {
-            int4* out = reinterpret_cast<int4*>(cand + (cloud0 + q) * TC_KP);
-#pragma unroll
-            for (int i = 0; i < TC_KP / 4; ++i) out[i] = make_int4(list[4 * i], list[4 * i + 1], list[4 * i + 2], list[4 * i + 3]);
-        }
+        if (row_ok) cand_n[cloud0 + qrow] = cnt;
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 5) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    if (warp == TC_WARP_MMA) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
     }
 }
 
-// ----------------------------------------------------------------------------------------------- re-rank
-// One warp per query: lane t evaluates candidate t exactly (same FP32 arithmetic as knn_feat_kernel),
-// the warp sorts, writes the k nearest and certifies the row.
+// ----------------------------------------------------------------------------------------------- finalize
+// One warp per query: sort the survivors by approximate distance, decide everything further than 2 err
+// from the kk-th by the approximation, re-evaluate the rest exactly (reference FP32 arithmetic).
 __global__ void __launch_bounds__(256)
-knn_tc_rerank_kernel(const float* __restrict__ x, int ldx, int N, long long P, int k, int self_loop, int diag_zero,
-                     int idx_bits, const int32_t* __restrict__ cand, const float* __restrict__ sqnorm,
-                     const float* __restrict__ cnorm, const int* __restrict__ cnorm_max_bits,
-                     int32_t* __restrict__ idx, float* __restrict__ dist2, uint8_t* __restrict__ redo) {
+knn_tc_finalize_kernel(const float* __restrict__ x, int ldx, int N, long long P, int k, int self_loop, int diag_zero,
+                       const int32_t* __restrict__ cand_j, const float* __restrict__ cand_d,
+                       const int32_t* __restrict__ cand_n, const float* __restrict__ sqnorm,
+                       const float* __restrict__ cnorm, const int* __restrict__ norm_max_bits,
+                       int32_t* __restrict__ idx, uint8_t* __restrict__ redo) {
     __shared__ float qd_all[8 * 64];
     __shared__ int qi_all[8 * 64];
     __shared__ float xq[8][TC_C];
@@ -338,55 +416,110 @@ knn_tc_rerank_kernel(const float* __restrict__ x, int ldx, int N, long long P, i
     const long long cloud0 = (long long)b * N;
     const int q = (int)(row - cloud0);
     const int kk = k + (self_loop ? 0 : 1);
-    const int idx_mask = (1 << idx_bits) - 1;
+    const int skip = self_loop ? 0 : 1;
+    const int n = __ldg(cand_n + row);
+    if (n > TC_CAP || n < kk) {        // overflow (or a NaN row): the exact kernel redoes this query
+        if (lane == 0) redo[row] = 1;
+        return;
+    }
+    if (lane == 0) redo[row] = 0;
 
+    FsWarpSelect<2> sel;
+    sel.init(qd_all + warp * 64, qi_all + warp * 64, 64);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int slot = h * 32 + lane;
+        const bool valid = slot < n;
+        const float d = valid ? __ldg(cand_d + row * TC_CAP + slot) : INFINITY;
+        const int j = valid ? __ldg(cand_j + row * TC_CAP + slot) : FS_IDX_PAD;
+        sel.offer(d, j, valid);
+    }
+    sel.finish();
+    float thr; int thr_j;
+    sel.get(kk - 1, thr, thr_j);
+    const float cmax = __int_as_float(__ldg(norm_max_bits + 2 * b)), rmax = __int_as_float(__ldg(norm_max_bits + 2 * b + 1));
+    const float qq = __ldg(sqnorm + row);
+    const float err = tc_row_err(__ldg(cnorm + row), cmax, qq, rmax);
+    const float lo = thr - 2.f * err, hi = thr + 2.f * err;
+
+    bool in_[2], amb[2];
+    int n_in = 0, n_amb = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const bool valid = sel.i[h] != FS_IDX_PAD;
+        in_[h] = valid && sel.d[h] < lo;
+        amb[h] = valid && !in_[h] && sel.d[h] <= hi;
+        n_in += __popc(__ballot_sync(FS_FULL_MASK, in_[h]));
+        n_amb += __popc(__ballot_sync(FS_FULL_MASK, amb[h]));
+    }
+    int32_t* out = idx + row * k;
+    const int slots = kk - n_in;
+    if (n_amb == slots) {
+        // the approximation alone decides the set: ranks [0, kk) in approximate order
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = h * 32 + lane;
+            if (r >= skip && r < kk) out[r - skip] = sel.i[h];
+        }
+        return;
+    }
+    // ambiguous boundary: exact distances (same arithmetic as knn_feat_kernel) for the ambiguous entries
     xq[warp][lane] = __ldg(x + row * ldx + lane);
     xq[warp][lane + 32] = __ldg(x + row * ldx + lane + 32);
     __syncwarp();
-    const int key = __ldg(cand + row * TC_KP + lane);
-    const bool valid = key != 0x7fffffff && (key & idx_mask) < N;
-    const int j = valid ? (key & idx_mask) : 0;
-    const float* xr = x + (cloud0 + j) * ldx;
-    float acc = 0.f;
+    float ex[2];
 #pragma unroll
-    for (int c4 = 0; c4 < TC_C / 4; ++c4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + c4);
-        acc = fmaf(xq[warp][4 * c4], v.x, acc);
-        acc = fmaf(xq[warp][4 * c4 + 1], v.y, acc);
-        acc = fmaf(xq[warp][4 * c4 + 2], v.z, acc);
-        acc = fmaf(xq[warp][4 * c4 + 3], v.w, acc);
+    for (int h = 0; h < 2; ++h) {
+        ex[h] = INFINITY;
+        if (amb[h]) {
+            const int j = sel.i[h];
+            const float* xr = x + (cloud0 + j) * ldx;
+            float acc = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < TC_C / 4; ++c4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + c4);
+                acc = fmaf(xq[warp][4 * c4], v.x, acc);
+                acc = fmaf(xq[warp][4 * c4 + 1], v.y, acc);
+                acc = fmaf(xq[warp][4 * c4 + 2], v.z, acc);
+                acc = fmaf(xq[warp][4 * c4 + 3], v.w, acc);
+            }
+            const float nj = __ldg(sqnorm + cloud0 + j);
+            float d = diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * acc), nj) : __fadd_rn(__fsub_rn(nj, 2.0f * acc), qq);
+            if (diag_zero && j == q) d = 0.f;
+            ex[h] = d;
+        }
     }
-    const float qq = __ldg(sqnorm + row), nj = __ldg(sqnorm + cloud0 + j);
-    float d = diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * acc), nj) : __fadd_rn(__fsub_rn(nj, 2.0f * acc), qq);
-    if (diag_zero && j == q) d = 0.f;
-
-    FsWarpSelect<1> sel;
-    sel.init(qd_all + warp * 64, qi_all + warp * 64, kk);
-    sel.offer(d, j, valid);
-    sel.finish();
-    sel.store(self_loop ? 0 : 1, idx + row * k, dist2 ? dist2 + row * k : nullptr, 0, 0, INFINITY);
-
-    // certificate: every non-candidate has approximate distance >= floor(key_KP) and the approximation is
-    // within err of the exact FP32 form, so it cannot beat the exact kk-th candidate if that is below bound.
-    float dk; int ik;
-    sel.get(kk - 1, dk, ik);
-    const int last_key = __shfl_sync(FS_FULL_MASK, key, TC_KP - 1);
-    const float approx_floor = __int_as_float(last_key & ~idx_mask);
-    const float cmax = __int_as_float(__ldg(cnorm_max_bits + b));
-    const float err = 6.2e-5f * (__ldg(cnorm + row) + cmax) + 4e-6f * (qq + __ldg(sqnorm + cloud0 + ik)) + 1e-30f;
-    const bool certified = (last_key == 0x7fffffff) /* fewer than KP points: everything was a candidate */
-                           || (ik != FS_IDX_PAD && dk < approx_floor - err);
-    if (lane == 0) redo[row] = certified ? 0 : 1;
+    // rank of every ambiguous entry among the ambiguous ones by exact (distance, index)
+    int rank[2] = {0, 0};
+    for (int src = 0; src < 64; ++src) {
+        const int sh = src >> 5, sl = src & 31;
+        const float sd = __shfl_sync(FS_FULL_MASK, sh ? ex[1] : ex[0], sl);
+        const int sj = __shfl_sync(FS_FULL_MASK, sh ? sel.i[1] : sel.i[0], sl);
+        const bool sa = __shfl_sync(FS_FULL_MASK, (int)(sh ? amb[1] : amb[0]), sl) != 0;
+        if (sa) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (amb[h] && fs_pair_less(sd, sj, ex[h], sel.i[h])) ++rank[h];
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int r = h * 32 + lane;
+        int pos = -1;
+        if (in_[h]) pos = r;                                   // sure-in entries occupy ranks [0, n_in)
+        else if (amb[h] && rank[h] < slots) pos = n_in + rank[h];
+        if (pos >= skip && pos < kk) out[pos - skip] = sel.i[h];
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_operand_map(EncodeTiledFn fn, CUtensorMap* map, void* base, long long rows) {
+int make_operand_map(EncodeTiledFn fn, CUtensorMap* map, void* base, long long rows, int box_rows) {
     const cuuint64_t dims[2] = {(cuuint64_t)TC_KROW, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)TC_KROW * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)TC_M};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -397,27 +530,28 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-// Declared in knn.cu: exact SIMT kernel restricted to the rows flagged in `redo`.
+// Defined in knn.cu.
 int fs_knn_feat_masked(cudaStream_t stream, const float* x, int ldx, int B, int N, int C, int k, int self_loop,
                        int diag_zero, int32_t* idx, float* dist2, const float* sqnorm, const uint8_t* redo);
-void fs_row_sqnorm(cudaStream_t stream, const float* x, int ldx, long long P, int C, float* out);
+int fs_knn_feat_exact(cudaStream_t stream, const float* x, int ldx, int B, int N, int C, int k, int self_loop,
+                      int diag_zero, int32_t* idx, float* dist2, float* sqnorm_ws);
 
 extern "C" size_t fs_knn_feat_tc_workspace_bytes(int B, int N, int C, int k) {
     (void)C; (void)k;
     const size_t P = (size_t)B * N;
     size_t bytes = 0;
     bytes += align_up(P * TC_KROW * 2, 256) * 2;        // A', B'
-    bytes += align_up(P * TC_KP * 4, 256);              // candidate keys
-    bytes += align_up(P * 4, 256) * 2;                  // exact norms, centred norms
+    bytes += align_up(P * TC_CAP * 4, 256) * 2;         // survivor indices, distances
+    bytes += align_up(P * 4, 256) * 3;                  // survivor counts, raw norms, centred norms
     bytes += align_up((size_t)B * TC_C * 4, 256);       // channel sums
-    bytes += align_up((size_t)B * 4, 256);              // max centred norm per cloud
+    bytes += align_up((size_t)B * 8, 256);              // max centred / raw norm per cloud
     bytes += align_up(P, 256);                          // redo flags
     return bytes;
 }
 
 extern "C" int fs_knn_feat_tc_supported(int B, int N, int C, int k, int self_loop) {
     const int kk = k + (self_loop ? 0 : 1);
-    return (C == TC_C && kk + 4 <= TC_KP && N >= TC_KP && N <= 8192 && (long long)B * N <= 0x7fffffff / TC_KROW) ? 1 : 0;
+    return (C == TC_C && kk <= TC_MAX_KK && N >= 2 * TC_NCLS && N <= 32768 && (long long)B * N <= 0x7fffffff / TC_KROW) ? 1 : 0;
 }
 
 extern "C" int fs_knn_feat_tc(int device, fs_stream_t stream_, const float* x, int ldx, int B, int N, int C, int k,
@@ -426,7 +560,8 @@ extern "C" int fs_knn_feat_tc(int device, fs_stream_t stream_, const float* x, i
     if (B < 0 || N <= 0 || k <= 0 || ldx < C) return FS_ERR_BAD_ARG;
     if (B == 0) return FS_OK;
     if (!x || !idx || !workspace) return FS_ERR_BAD_ARG;
-    if (!fs_knn_feat_tc_supported(B, N, C, k, self_loop)) return FS_ERR_UNSUPPORTED;
+    const int kk = k + (self_loop ? 0 : 1);
+    if (kk > N || kk > FS_MAX_K + 1) return FS_ERR_BAD_ARG;
     if (workspace_bytes < fs_knn_feat_tc_workspace_bytes(B, N, C, k)) return FS_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (ldx & 3) || (reinterpret_cast<uintptr_t>(workspace) & 255)) return FS_ERR_ALIGNMENT;
     FS_ENTER(device);
@@ -436,12 +571,18 @@ extern "C" int fs_knn_feat_tc(int device, fs_stream_t stream_, const float* x, i
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(ws); ws += align_up((size_t)P * TC_KROW * 2, 256);
     __nv_bfloat16* Bm = reinterpret_cast<__nv_bfloat16*>(ws); ws += align_up((size_t)P * TC_KROW * 2, 256);
-    int32_t* cand = reinterpret_cast<int32_t*>(ws); ws += align_up((size_t)P * TC_KP * 4, 256);
+    int32_t* cand_j = reinterpret_cast<int32_t*>(ws); ws += align_up((size_t)P * TC_CAP * 4, 256);
+    float* cand_d = reinterpret_cast<float*>(ws); ws += align_up((size_t)P * TC_CAP * 4, 256);
+    int32_t* cand_n = reinterpret_cast<int32_t*>(ws); ws += align_up((size_t)P * 4, 256);
     float* sqnorm = reinterpret_cast<float*>(ws); ws += align_up((size_t)P * 4, 256);
     float* cnorm = reinterpret_cast<float*>(ws); ws += align_up((size_t)P * 4, 256);
     float* sums = reinterpret_cast<float*>(ws); ws += align_up((size_t)B * TC_C * 4, 256);
-    int* cmax = reinterpret_cast<int*>(ws); ws += align_up((size_t)B * 4, 256);
+    int* nmax = reinterpret_cast<int*>(ws); ws += align_up((size_t)B * 8, 256);
     uint8_t* redo = ws;
+
+    // distances requested (public knn(..., return_dist=True)) or shape outside the tensor-core path: exact kernel
+    if (dist2 || !fs_knn_feat_tc_supported(B, N, C, k, self_loop))
+        return fs_knn_feat_exact(stream, x, ldx, B, N, C, k, self_loop, diag_zero, idx, dist2, sqnorm);
 
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -452,30 +593,27 @@ extern "C" int fs_knn_feat_tc(int device, fs_stream_t stream_, const float* x, i
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
     CUtensorMap map_a, map_b;
-    int e = make_operand_map(encode, &map_a, A, P);
+    int e = make_operand_map(encode, &map_a, A, P, TC_M);
     if (e) return e;
-    e = make_operand_map(encode, &map_b, Bm, P);
+    e = make_operand_map(encode, &map_b, Bm, P, TC_NB);
     if (e) return e;
 
     // 1. prep
-    FS_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)B * TC_C * 4 + 0, stream));
-    FS_CUDA_TRY(cudaMemsetAsync(cmax, 0, (size_t)B * 4, stream));
+    FS_CUDA_TRY(cudaMemsetAsync(sums, 0, align_up((size_t)B * TC_C * 4, 256) + (size_t)B * 8, stream));
     tc_colsum_kernel<<<dim3(16, B), 256, 0, stream>>>(x, ldx, N, sums);
-    tc_split_kernel<<<fs_div_up(P, 8), 256, 0, stream>>>(x, ldx, P, N, sums, A, Bm, cnorm, cmax);
-    fs_row_sqnorm(stream, x, ldx, P, C, sqnorm);
+    tc_split_kernel<<<fs_div_up(P, 8), 256, 0, stream>>>(x, ldx, P, N, sums, A, Bm, cnorm, sqnorm, nmax);
     FS_RETURN_IF_LAUNCH_FAILED();
 
-    // 2. tensor-core candidate search
-    int idx_bits = 1;
-    while ((1 << idx_bits) < N) ++idx_bits;
-    FS_CUDA_TRY(cudaFuncSetAttribute(knn_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    dim3 grid(fs_div_up(N, TC_M), B);
-    knn_tc_candidates_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map_a, map_b, N, idx_bits, cand);
+    // 2. tensor-core sweeps
+    FS_CUDA_TRY(cudaFuncSetAttribute(knn_tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    dim3 grid(fs_div_up(N, TC_QT * TC_M), B);
+    knn_tc_select_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map_a, map_b, N, kk, diag_zero, cnorm, sqnorm, nmax,
+                                                                      cand_j, cand_d, cand_n);
     FS_RETURN_IF_LAUNCH_FAILED();
 
-    // 3. exact re-rank + certificate, then the exact kernel on uncertified rows
-    knn_tc_rerank_kernel<<<fs_div_up(P, 8), 256, 0, stream>>>(x, ldx, N, P, k, self_loop, diag_zero, idx_bits, cand, sqnorm,
-                                                              cnorm, cmax, idx, dist2, redo);
+    // 3. finalize, then the exact kernel on rows whose survivor list overflowed
+    knn_tc_finalize_kernel<<<fs_div_up(P, 8), 256, 0, stream>>>(x, ldx, N, P, k, self_loop, diag_zero, cand_j, cand_d, cand_n,
+                                                                sqnorm, cnorm, nmax, idx, redo);
     FS_RETURN_IF_LAUNCH_FAILED();
-    return fs_knn_feat_masked(stream, x, ldx, B, N, C, k, self_loop, diag_zero, idx, dist2, sqnorm, redo);
+    return fs_knn_feat_masked(stream, x, ldx, B, N, C, k, self_loop, diag_zero, idx, nullptr, sqnorm, redo);
 }

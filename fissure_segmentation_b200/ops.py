@@ -77,7 +77,7 @@ def knn_features(feat, B, N, k, self_loop=False, diag_zero=True, return_dist=Fal
     if B == 0:
         return (idx, dist) if return_dist else idx
     lib = _lib.load()
-    if (USE_TENSOR_CORE_KNN and feat.stride(0) % 4 == 0 and feat.data_ptr() % 16 == 0
+    if (USE_TENSOR_CORE_KNN and not return_dist and feat.stride(0) % 4 == 0 and feat.data_ptr() % 16 == 0
             and lib.fs_knn_feat_tc_supported(B, N, C, k, int(self_loop))):
         # tcgen05 candidate search + exact FP32 re-rank (same result as the exact kernel)
         nbytes = lib.fs_knn_feat_tc_workspace_bytes(B, N, C, k)
