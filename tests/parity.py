@@ -19,6 +19,11 @@ def compare_knn(idx_gpu, dist_gpu, x_bcn_cpu, k, self_loop, oracle_knn_with_gap)
     gap = (next_d - ref_d[..., -1]).unsqueeze(-1)
     # also ties inside the kept list do not matter for sets; only the boundary does
     tie_row = (gap <= scale).squeeze(-1)
+    if not self_loop:
+        # the reference drops column 0 of a k+1 search (general_utils.py:317-322); when the two smallest
+        # distances are within rounding of each other (duplicate keypoints) WHICH point is dropped is arbitrary
+        _, d01, _, _ = oracle_knn_with_gap(x_bcn_cpu, 2, True)
+        tie_row |= ((d01[..., 1] - d01[..., 0]).unsqueeze(-1) <= scale).squeeze(-1)
     same_set = (gi.sort(dim=-1)[0] == ref_i.sort(dim=-1)[0]).all(dim=-1)
     report = {
         "rows": B * N,
