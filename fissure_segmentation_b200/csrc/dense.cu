@@ -1,0 +1,449 @@
+// BatchNorm + LeakyReLU on point-major tables (the dense layers around the EdgeConvs: SharedFullyConnected
+// with dim=1, models/dgcnn.py:282-323, used at :123-137) and the fused global max-pool
+// (AdaptiveMaxPool1d after Conv1d+BN+LeakyReLU, models/dgcnn.py:123-126, 156).
+//
+// The 1x1 convolutions themselves are cuBLAS GEMMs; these kernels replace the BatchNorm / activation /
+// pooling passes around them: column statistics in one read, normalise+activate in one read+write, and for
+// the global feature only per-cloud max/min of the GEMM output is kept (LeakyReLU(BN(.)) is monotone), so the
+// B*N x 1024 activation is never written.
+//
+// An optional per-cloud row bias (B x C, fp32) is added to x on load: segmentation[0] acts on
+// [local | broadcast global] (models/dgcnn.py:159), i.e. local GEMM + one bias row per cloud.
+#include "fs_common.cuh"
+
+namespace {
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    __device__ __forceinline__ static void load(const float* p, float* f) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    }
+    __device__ __forceinline__ static void store(float* p, const float* f) {
+        *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+};
+template <> struct Vec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    __device__ __forceinline__ static void load(const __nv_bfloat16* p, float* f) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        fs_bf16x8_to_float(v, f);
+    }
+    __device__ __forceinline__ static void store(__nv_bfloat16* p, const float* f) {
+        uint4 v;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = v;
+    }
+};
+
+constexpr int DN_THREADS = 256;
+
+// thread -> (row within block pass, channel vector). tpr = threads per row = C / VEC (power of two, <= 256)
+struct RowMap {
+    int tpr, rows_per_pass, r, c0;
+    __device__ RowMap(int C, int vec) {
+        tpr = C / vec;
+        if (tpr > DN_THREADS) tpr = DN_THREADS;
+        rows_per_pass = DN_THREADS / tpr;
+        r = threadIdx.x / tpr;
+        c0 = (threadIdx.x - r * tpr) * vec;
+    }
+};
+
+template <int V>
+__device__ __forceinline__ void add_bias(float* f, const float* __restrict__ bias, long long row, int N, int C, int c) {
+    if (bias) {
+        const float* bp = bias + (row / N) * C + c;
+#pragma unroll
+        for (int i = 0; i < V; ++i) f[i] += __ldg(bp + i);
+    }
+}
+
+// Per-column sums of (x - pivot), (x - pivot)^2 in fp64; pivot = row 0. stats = [S1 | S2 | pivot], each C.
+template <typename T>
+__global__ void __launch_bounds__(DN_THREADS)
+colstats_kernel(const T* __restrict__ x, int ld, long long rows, int C, const float* __restrict__ bias, int N,
+                double* __restrict__ stats) {
+    constexpr int V = Vec<T>::N;
+    extern __shared__ double red[];     // [2*C]
+    RowMap m(C, V);
+    for (int c = threadIdx.x; c < 2 * C; c += DN_THREADS) red[c] = 0.0;
+    __syncthreads();
+    for (int cc = m.c0; cc < C; cc += m.tpr * V) {
+        float piv[V];
+        Vec<T>::load(x + cc, piv);
+        add_bias<V>(piv, bias, 0, N, C, cc);
+        float s1[V], s2[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += (long long)gridDim.x * m.rows_per_pass) {
+            float f[V];
+            Vec<T>::load(x + row * ld + cc, f);
+            add_bias<V>(f, bias, row, N, C, cc);
+#pragma unroll
+            for (int i = 0; i < V; ++i) { const float d = f[i] - piv[i]; s1[i] += d; s2[i] = fmaf(d, d, s2[i]); }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) { atomicAdd(&red[cc + i], (double)s1[i]); atomicAdd(&red[C + cc + i], (double)s2[i]); }
+        if (blockIdx.x == 0 && m.r == 0) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) stats[2 * C + cc + i] = (double)piv[i];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += DN_THREADS) atomicAdd(&stats[c], red[c]);
+}
+
+// y = LeakyReLU(scale * (x - mu) + beta)
+template <typename T, typename OT>
+__global__ void __launch_bounds__(DN_THREADS)
+bn_act_apply_kernel(const T* __restrict__ x, int ld, long long rows, int C, const float* __restrict__ bias, int N,
+                    const float* __restrict__ coef, float slope, OT* __restrict__ out, int ld_out) {
+    constexpr int V = Vec<T>::N;
+    RowMap m(C, V);
+    for (int cc = m.c0; cc < C; cc += m.tpr * V) {
+        float mu[V], sc[V], be[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) { mu[i] = __ldg(coef + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i); be[i] = __ldg(coef + 3 * C + cc + i); }
+        for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += (long long)gridDim.x * m.rows_per_pass) {
+            float f[V];
+            Vec<T>::load(x + row * ld + cc, f);
+            add_bias<V>(f, bias, row, N, C, cc);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float z = fmaf(sc[i], f[i] - mu[i], be[i]);
+                f[i] = z > 0.f ? z : slope * z;
+            }
+            if (V == 8 && sizeof(OT) == 4) {
+                Vec<float>::store(reinterpret_cast<float*>(out) + row * ld_out + cc, f);
+                Vec<float>::store(reinterpret_cast<float*>(out) + row * ld_out + cc + 4, f + 4);
+            } else if (V == 4 && sizeof(OT) == 2) {
+                uint2 v;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+                h[0] = __floats2bfloat162_rn(f[0], f[1]);
+                h[1] = __floats2bfloat162_rn(f[2], f[3]);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * ld_out + cc) = v;
+            } else {
+                Vec<OT>::store(out + row * ld_out + cc, f);
+            }
+        }
+    }
+}
+
+// d = g * LeakyReLU'(z); dgb = [sum d | sum d * xhat] in fp64
+template <typename GT, typename T>
+__global__ void __launch_bounds__(DN_THREADS)
+bn_act_bwd_reduce_kernel(const GT* __restrict__ g, int ldg, const T* __restrict__ x, int ld, long long rows, int C,
+                         const float* __restrict__ bias, int N, const float* __restrict__ coef, float slope,
+                         double* __restrict__ dgb) {
+    constexpr int V = 4;
+    extern __shared__ double red[];
+    RowMap m(C, V);
+    for (int c = threadIdx.x; c < 2 * C; c += DN_THREADS) red[c] = 0.0;
+    __syncthreads();
+    for (int cc = m.c0; cc < C; cc += m.tpr * V) {
+        float mu[V], inv[V], sc[V], be[V], s1[V], s2[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            mu[i] = __ldg(coef + cc + i); inv[i] = __ldg(coef + C + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i);
+            be[i] = __ldg(coef + 3 * C + cc + i); s1[i] = 0.f; s2[i] = 0.f;
+        }
+        for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += (long long)gridDim.x * m.rows_per_pass) {
+            float gv[V], f[V];
+            if (sizeof(GT) == 4) Vec<float>::load(reinterpret_cast<const float*>(g) + row * ldg + cc, gv);
+            else {
+                uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g) + row * ldg + cc));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
+                gv[0] = a.x; gv[1] = a.y; gv[2] = b2.x; gv[3] = b2.y;
+            }
+            if (sizeof(T) == 4) Vec<float>::load(reinterpret_cast<const float*>(x) + row * ld + cc, f);
+            else {
+                uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + row * ld + cc));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
+                f[0] = a.x; f[1] = a.y; f[2] = b2.x; f[3] = b2.y;
+            }
+            add_bias<V>(f, bias, row, N, C, cc);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float xc = f[i] - mu[i];
+                const float z = fmaf(sc[i], xc, be[i]);
+                const float d = z > 0.f ? gv[i] : slope * gv[i];
+                s1[i] += d;
+                s2[i] = fmaf(d, xc * inv[i], s2[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) { atomicAdd(&red[cc + i], (double)s1[i]); atomicAdd(&red[C + cc + i], (double)s2[i]); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += DN_THREADS) atomicAdd(&dgb[c], red[c]);
+}
+
+// dx = scale * (d - dbeta/M - xhat * dgamma/M)      (train_stats = 0: dx = scale * d)
+template <typename GT, typename T, typename OT>
+__global__ void __launch_bounds__(DN_THREADS)
+bn_act_bwd_apply_kernel(const GT* __restrict__ g, int ldg, const T* __restrict__ x, int ld, long long rows, int C,
+                        const float* __restrict__ bias, int N, const float* __restrict__ coef, float slope,
+                        const double* __restrict__ dgb, double count, int train_stats, OT* __restrict__ dx, int ld_dx) {
+    constexpr int V = 4;
+    RowMap m(C, V);
+    for (int cc = m.c0; cc < C; cc += m.tpr * V) {
+        float mu[V], inv[V], sc[V], be[V], mb[V], mg[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            mu[i] = __ldg(coef + cc + i); inv[i] = __ldg(coef + C + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i);
+            be[i] = __ldg(coef + 3 * C + cc + i);
+            mb[i] = train_stats ? (float)(dgb[cc + i] / count) : 0.f;
+            mg[i] = train_stats ? (float)(dgb[C + cc + i] / count) * inv[i] : 0.f;
+        }
+        for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += (long long)gridDim.x * m.rows_per_pass) {
+            float gv[V], f[V], o[V];
+            if (sizeof(GT) == 4) Vec<float>::load(reinterpret_cast<const float*>(g) + row * ldg + cc, gv);
+            else {
+                uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g) + row * ldg + cc));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
+                gv[0] = a.x; gv[1] = a.y; gv[2] = b2.x; gv[3] = b2.y;
+            }
+            if (sizeof(T) == 4) Vec<float>::load(reinterpret_cast<const float*>(x) + row * ld + cc, f);
+            else {
+                uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + row * ld + cc));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
+                f[0] = a.x; f[1] = a.y; f[2] = b2.x; f[3] = b2.y;
+            }
+            add_bias<V>(f, bias, row, N, C, cc);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float xc = f[i] - mu[i];
+                const float z = fmaf(sc[i], xc, be[i]);
+                const float d = z > 0.f ? gv[i] : slope * gv[i];
+                o[i] = sc[i] * (d - mb[i] - mg[i] * xc);
+            }
+            if (sizeof(OT) == 4) Vec<float>::store(reinterpret_cast<float*>(dx) + row * ld_dx + cc, o);
+            else {
+                uint2 v;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+                h[0] = __floats2bfloat162_rn(o[0], o[1]);
+                h[1] = __floats2bfloat162_rn(o[2], o[3]);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dx) + row * ld_dx + cc) = v;
+            }
+        }
+    }
+}
+
+// Global max-pool fused with the statistics: per cloud and channel, max (gamma >= 0) or min (gamma < 0) of x over the
+// N rows, its row index, and the column sums. grid = (C / 64, B); block = 4 row-groups x 64 channels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_reduce_kernel(const T* __restrict__ x, int ld, int N, int C, const float* __restrict__ gamma,
+                   float* __restrict__ sel, int32_t* __restrict__ arg, double* __restrict__ stats) {
+    __shared__ float s_best[4][64];
+    __shared__ int s_arg[4][64];
+    __shared__ float s_1[4][64], s_2[4][64];
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int rg = threadIdx.x >> 6;
+    const bool use_max = __ldg(gamma + c) >= 0.f;
+    const T* xb = x + (long long)b * N * ld + c;
+    const float piv = stats ? (float)x[c] : 0.f;        // row 0 of the whole table
+    float best = use_max ? -INFINITY : INFINITY;
+    int barg = 0;
+    float f1 = 0.f, f2 = 0.f;
+    for (int r = rg; r < N; r += 4) {
+        const float v = (float)xb[(long long)r * ld];
+        const bool better = use_max ? (v > best) : (v < best);
+        if (better) { best = v; barg = r; }
+        const float d = v - piv;
+        f1 += d;
+        f2 = fmaf(d, d, f2);
+    }
+    s_best[rg][threadIdx.x & 63] = best; s_arg[rg][threadIdx.x & 63] = barg;
+    s_1[rg][threadIdx.x & 63] = f1; s_2[rg][threadIdx.x & 63] = f2;
+    __syncthreads();
+    if (rg == 0) {
+        const int t = threadIdx.x;
+        double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float v = s_best[g][t];
+            const int a = s_arg[g][t];
+            const bool better = use_max ? (v > best || (v == best && a < barg)) : (v < best || (v == best && a < barg));
+            if (g > 0 && better) { best = v; barg = a; }
+            a1 += (double)s_1[g][t]; a2 += (double)s_2[g][t];
+        }
+        sel[(long long)b * C + c] = best;
+        arg[(long long)b * C + c] = barg;
+        if (stats) {
+            atomicAdd(&stats[c], a1);
+            atomicAdd(&stats[C + c], a2);
+            if (b == 0) stats[2 * C + c] = (double)piv;
+        }
+    }
+}
+
+// dX[r, c] = scale * ( [r == arg[b,c]] * d[b,c] - dbeta/M - xhat[r,c] * dgamma/M ),  d = g * LeakyReLU'(z_sel)
+template <typename T, typename OT>
+__global__ void __launch_bounds__(DN_THREADS)
+pool_bwd_kernel(const T* __restrict__ x, int ld, int N, long long rows, int C, const float* __restrict__ g,
+                const float* __restrict__ sel, const int32_t* __restrict__ arg, const float* __restrict__ coef, float slope,
+                const double* __restrict__ dgb, double count, int train_stats, OT* __restrict__ dx, int ld_dx) {
+    constexpr int V = 4;
+    RowMap m(C, V);
+    for (int cc = m.c0; cc < C; cc += m.tpr * V) {
+        float mu[V], inv[V], sc[V], be[V], mb[V], mg[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            mu[i] = __ldg(coef + cc + i); inv[i] = __ldg(coef + C + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i);
+            be[i] = __ldg(coef + 3 * C + cc + i);
+            mb[i] = train_stats ? (float)(dgb[cc + i] / count) : 0.f;
+            mg[i] = train_stats ? (float)(dgb[C + cc + i] / count) * inv[i] : 0.f;
+        }
+        for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += (long long)gridDim.x * m.rows_per_pass) {
+            const long long b = row / N;
+            const int r = (int)(row - b * N);
+            float f[V], o[V];
+            if (sizeof(T) == 4) Vec<float>::load(reinterpret_cast<const float*>(x) + row * ld + cc, f);
+            else {
+                uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + row * ld + cc));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
+                f[0] = a.x; f[1] = a.y; f[2] = b2.x; f[3] = b2.y;
+            }
+            const int4 av = __ldg(reinterpret_cast<const int4*>(arg + b * C + cc));
+            const int ar[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                float routed = 0.f;
+                if (ar[i] == r) {
+                    const float zs = fmaf(sc[i], __ldg(sel + b * C + cc + i) - mu[i], be[i]);
+                    const float gv = __ldg(g + b * C + cc + i);
+                    routed = zs > 0.f ? gv : slope * gv;
+                }
+                o[i] = train_stats ? sc[i] * (routed - mb[i] - mg[i] * (f[i] - mu[i])) : sc[i] * routed;
+            }
+            if (sizeof(OT) == 4) Vec<float>::store(reinterpret_cast<float*>(dx) + row * ld_dx + cc, o);
+            else {
+                uint2 v;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+                h[0] = __floats2bfloat162_rn(o[0], o[1]);
+                h[1] = __floats2bfloat162_rn(o[2], o[3]);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dx) + row * ld_dx + cc) = v;
+            }
+        }
+    }
+}
+
+int dn_grid(long long rows, int rows_per_pass) {
+    long long need = (rows + rows_per_pass - 1) / rows_per_pass;
+    const long long cap = (long long)FS_NUM_SMS * 8;
+    return (int)(need < 1 ? 1 : (need > cap ? cap : need));
+}
+bool pow2_width(int C, int vec) { return C >= 64 && C <= 4096 && (C & (C - 1)) == 0 && C % vec == 0; }
+int rows_per_pass(int C, int vec) { int tpr = C / vec; if (tpr > DN_THREADS) tpr = DN_THREADS; return DN_THREADS / tpr; }
+
+}  // namespace
+
+extern "C" int fs_colstats(int device, fs_stream_t stream_, const void* x, int dtype, int ld, long long rows, int C,
+                           const float* rowbias, int N, double* stats) {
+    if (!x || !stats || rows <= 0 || ld < C || (rowbias && N <= 0)) return FS_ERR_BAD_ARG;
+    const int vec = dtype == FS_BF16 ? 8 : 4;
+    if (!pow2_width(C, vec)) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int grid = dn_grid(rows, rows_per_pass(C, vec));
+    const size_t smem = (size_t)2 * C * sizeof(double);
+    if (dtype == FS_BF16) colstats_kernel<<<grid, DN_THREADS, smem, stream>>>((const __nv_bfloat16*)x, ld, rows, C, rowbias, N, stats);
+    else colstats_kernel<<<grid, DN_THREADS, smem, stream>>>((const float*)x, ld, rows, C, rowbias, N, stats);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_bn_act_apply(int device, fs_stream_t stream_, const void* x, int dtype, int ld, long long rows, int C,
+                               const float* rowbias, int N, const float* coef, float slope, void* out, int out_dtype,
+                               int ld_out) {
+    if (!x || !coef || !out || rows <= 0 || ld < C || ld_out < C || (rowbias && N <= 0)) return FS_ERR_BAD_ARG;
+    const int vec = dtype == FS_BF16 ? 8 : 4;
+    if (!pow2_width(C, vec)) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int grid = dn_grid(rows, rows_per_pass(C, vec));
+#define GO(T, OT) bn_act_apply_kernel<<<grid, DN_THREADS, 0, stream>>>((const T*)x, ld, rows, C, rowbias, N, coef, slope, (OT*)out, ld_out)
+    if (dtype == FS_BF16 && out_dtype == FS_BF16) GO(__nv_bfloat16, __nv_bfloat16);
+    else if (dtype == FS_BF16) GO(__nv_bfloat16, float);
+    else if (out_dtype == FS_BF16) GO(float, __nv_bfloat16);
+    else GO(float, float);
+#undef GO
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_bn_act_bwd(int device, fs_stream_t stream_, const void* g, int g_dtype, int ldg, const void* x, int dtype,
+                             int ld, long long rows, int C, const float* rowbias, int N, const float* coef, float slope,
+                             double* dgb, double count, int train_stats, void* dx, int dx_dtype, int ld_dx) {
+    if (!g || !x || !coef || !dgb || rows <= 0 || ld < C || ldg < C || (dx && ld_dx < C) || count <= 0) return FS_ERR_BAD_ARG;
+    if (!pow2_width(C, 4)) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int grid = dn_grid(rows, rows_per_pass(C, 4));
+    const size_t smem = (size_t)2 * C * sizeof(double);
+#define RED(GT, T) bn_act_bwd_reduce_kernel<<<grid, DN_THREADS, smem, stream>>>((const GT*)g, ldg, (const T*)x, ld, rows, C, rowbias, N, coef, slope, dgb)
+    if (g_dtype == FS_BF16 && dtype == FS_BF16) RED(__nv_bfloat16, __nv_bfloat16);
+    else if (g_dtype == FS_BF16) RED(__nv_bfloat16, float);
+    else if (dtype == FS_BF16) RED(float, __nv_bfloat16);
+    else RED(float, float);
+#undef RED
+    FS_RETURN_IF_LAUNCH_FAILED();
+    if (!dx) return FS_OK;      // reduction only (pooled layers: the dense gradient is written by fs_pool_bwd)
+#define APP(GT, T, OT) bn_act_bwd_apply_kernel<<<grid, DN_THREADS, 0, stream>>>((const GT*)g, ldg, (const T*)x, ld, rows, C, rowbias, N, coef, slope, dgb, count, train_stats, (OT*)dx, ld_dx)
+    const bool gb = g_dtype == FS_BF16, xb = dtype == FS_BF16, ob = dx_dtype == FS_BF16;
+    if (gb && xb && ob) APP(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
+    else if (gb && xb) APP(__nv_bfloat16, __nv_bfloat16, float);
+    else if (gb && ob) APP(__nv_bfloat16, float, __nv_bfloat16);
+    else if (gb) APP(__nv_bfloat16, float, float);
+    else if (xb && ob) APP(float, __nv_bfloat16, __nv_bfloat16);
+    else if (xb) APP(float, __nv_bfloat16, float);
+    else if (ob) APP(float, float, __nv_bfloat16);
+    else APP(float, float, float);
+#undef APP
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_pool_reduce(int device, fs_stream_t stream_, const void* x, int dtype, int ld, int B, int N, int C,
+                              const float* gamma, float* sel, int32_t* arg, double* stats) {
+    if (!x || !gamma || !sel || !arg || B <= 0 || N <= 0 || ld < C) return FS_ERR_BAD_ARG;
+    if (C % 64) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    dim3 grid(C / 64, B);
+    if (dtype == FS_BF16) pool_reduce_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, N, C, gamma, sel, arg, stats);
+    else pool_reduce_kernel<<<grid, 256, 0, stream>>>((const float*)x, ld, N, C, gamma, sel, arg, stats);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_pool_bwd(int device, fs_stream_t stream_, const void* x, int dtype, int ld, int B, int N, int C,
+                           const float* g, const float* sel, const int32_t* arg, const float* coef, float slope,
+                           const double* dgb, double count, int train_stats, void* dx, int dx_dtype, int ld_dx) {
+    if (!x || !g || !sel || !arg || !coef || !dx || B <= 0 || N <= 0 || ld < C || ld_dx < C) return FS_ERR_BAD_ARG;
+    if (train_stats && (!dgb || count <= 0)) return FS_ERR_BAD_ARG;
+    if (!pow2_width(C, 4)) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long rows = (long long)B * N;
+    const int grid = dn_grid(rows, rows_per_pass(C, 4));
+#define GO(T, OT) pool_bwd_kernel<<<grid, DN_THREADS, 0, stream>>>((const T*)x, ld, N, rows, C, g, sel, arg, coef, slope, dgb, count, train_stats, (OT*)dx, ld_dx)
+    if (dtype == FS_BF16 && dx_dtype == FS_BF16) GO(__nv_bfloat16, __nv_bfloat16);
+    else if (dtype == FS_BF16) GO(__nv_bfloat16, float);
+    else if (dx_dtype == FS_BF16) GO(float, __nv_bfloat16);
+    else GO(float, float);
+#undef GO
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}

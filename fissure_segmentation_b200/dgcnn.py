@@ -85,9 +85,16 @@ class ConvBlock(nn.Module):
         w = self.conv.weight
         return w.view(w.shape[0], w.shape[1])
 
-    def norm_act_pm(self, y):
-        """BatchNorm (over all rows) + LeakyReLU on a point-major (rows, C) table."""
+    def norm_act_pm(self, y, rowbias=None, rows_per_cloud=1):
+        """BatchNorm (over all rows) + LeakyReLU on a point-major (rows, C) table; `rowbias` (B, C) is an
+        optional per-cloud bias added to y first (fused into the kernels)."""
         bn = self.norm
+        C = y.shape[1]
+        if bn is not None and y.is_cuda and C >= 64 and (C & (C - 1)) == 0 and y.stride(1) == 1:
+            slope = self.negative_slope if self.has_activation else 1.0
+            return ops.bn_act(y, bn, slope, rowbias, rows_per_cloud)
+        if rowbias is not None:
+            y = (y.view(-1, rows_per_cloud, C) + rowbias.to(y.dtype).unsqueeze(1)).view(-1, C)
         if bn is not None:
             y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps)
             if bn.training:
@@ -95,6 +102,18 @@ class ConvBlock(nn.Module):
         if self.has_activation:
             y = F.leaky_relu(y, self.negative_slope)
         return y
+
+    def forward_pool_pm(self, x, B, N):
+        """Conv + BatchNorm + LeakyReLU followed by the max over the N points of each cloud -> (B, C_out).
+        LeakyReLU(BN(.)) is monotone per channel, so only per-cloud max/min of the GEMM output is needed."""
+        y = x @ self.weight_matrix().to(x.dtype).t()
+        bn = self.norm
+        C = y.shape[1]
+        if bn is not None and self.conv.bias is None and y.is_cuda and C >= 64 and (C & (C - 1)) == 0:
+            return ops.pool_bn_act(y, bn, self.negative_slope if self.has_activation else 1.0, B, N)
+        if self.conv.bias is not None:
+            y = y + self.conv.bias.to(y.dtype)
+        return self.norm_act_pm(y).view(B, N, -1).amax(dim=1)
 
     def forward_pm(self, x):
         """x (rows, C_in) -> (rows, C_out): 1x1 conv as a GEMM, then BatchNorm + LeakyReLU."""
@@ -202,8 +221,7 @@ class SpatialTransformer(nn.Module):
         with torch.autocast("cuda", enabled=False):
             cdt = _compute_dtype(self.ec.precision)
             feat = self.ec.forward_pm(ops.to_point_major(coords), B, N, _as_graph(fixed_knn_graph), cdt)
-            feat = self.shared_fc.forward_pm(feat.to(cdt))              # (B*N, 1024)
-            feat = feat.view(B, N, -1).amax(dim=1).float()              # max over points
+            feat = self.shared_fc.forward_pool_pm(feat.to(cdt), B, N).float()   # conv + BN + LReLU + max over points
             mat = self.transform(self.mlp(feat)).view(B, self.in_features, self.in_features)
             moved = torch.bmm(coords.transpose(2, 1), mat).transpose(2, 1)
         return torch.cat([moved.to(x.dtype), x[:, self.in_features:]], dim=1)
@@ -307,8 +325,7 @@ class DGCNNSeg(DGCNNBase):
             x3 = self.ec3.forward_pm(x2, B, N, g, cdt)
             feats = torch.cat([x1, x2, x3], dim=1).to(cdt)                       # (B*N, 192)
 
-            glob = self.global_feature[0].forward_pm(feats)                      # (B*N, 1024)
-            glob = glob.view(B, N, -1).amax(dim=1)                               # (B, 1024)
+            glob = self.global_feature[0].forward_pool_pm(feats, B, N)           # (B, 1024), activation never written
 
             # segmentation[0] on [feats | broadcast global]: split the weight instead of materialising
             # the 1216-wide concat (models/dgcnn.py:159): local GEMM + one per-cloud bias row
@@ -316,7 +333,7 @@ class DGCNNSeg(DGCNNBase):
             w0 = seg0.weight_matrix().to(cdt)
             local = feats @ w0[:, :feats.shape[1]].t()
             per_cloud = glob @ w0[:, feats.shape[1]:].t()                        # (B, 256)
-            h = seg0.norm_act_pm((local.view(B, N, -1) + per_cloud.unsqueeze(1)).view(B * N, -1))
+            h = seg0.norm_act_pm(local, rowbias=per_cloud, rows_per_cloud=N)
             h = self.segmentation[1].forward_pm(h)
             h = self.segmentation[2].forward_pm(h)
             logits = self.segmentation[3].forward_pm(h)                          # (B*N, classes)
@@ -353,7 +370,7 @@ class DGCNNReg(DGCNNBase):
             x3 = self.ec3.forward_pm(x2, B, N, g, cdt)
             x4 = self.ec4.forward_pm(x3, B, N, g, cdt)
             feats = torch.cat([x1, x2, x3, x4], dim=1).to(cdt)
-            glob = self.global_feature[0].forward_pm(feats).view(B, N, -1).amax(dim=1)   # (B, 1024)
+            glob = self.global_feature[0].forward_pool_pm(feats, B, N)                   # (B, 1024)
             h = glob
             for layer in self.regression:
                 h = layer.forward_pm(h)

@@ -316,3 +316,102 @@ def nn_points(x, y):
     i = torch.empty(B, N, dtype=torch.int32, device=x.device)
     _lib.call("fs_nn_points", x, x, y, B, N, y.shape[1], d, i)
     return d, i
+
+
+# ------------------------------------------------------------------------------------------- dense layers
+
+def _col_bn_coef(x, rows, C, rowbias, N, gamma32, beta32, bn, training):
+    """Batch statistics of the columns of x (train) or running statistics (eval) -> coef [mu|invstd|scale|beta]."""
+    if training:
+        stats = torch.zeros(3 * C, dtype=torch.float64, device=x.device)
+        _lib.call("fs_colstats", x, x, _lib.dtype_code(x), x.stride(0), rows, C, rowbias, N, stats)
+    else:
+        stats = None
+    return stats
+
+
+class _BnActFn(torch.autograd.Function):
+    """y = LeakyReLU(BatchNorm(x + rowbias[cloud])) on a point-major table (SharedFullyConnected, dim=1:
+    models/dgcnn.py:306-315 after the 1x1 conv). Statistics over all rows, fp64 accumulation."""
+
+    @staticmethod
+    def forward(ctx, x, rowbias, gamma, beta, running_mean, running_var, nbt, training, eps, momentum, slope, N):
+        rows, C = x.shape
+        gamma32, beta32 = gamma.detach().float(), beta.detach().float()
+        rb = rowbias.detach().float().contiguous() if rowbias is not None else None
+        stats = None
+        if training:
+            stats = torch.zeros(3 * C, dtype=torch.float64, device=x.device)
+            _lib.call("fs_colstats", x, x, _lib.dtype_code(x), x.stride(0), rows, C, rb, N, stats)
+        coef = _bn_coef(x, stats, rows, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
+        out = torch.empty(rows, C, dtype=x.dtype, device=x.device)
+        _lib.call("fs_bn_act_apply", x, x, _lib.dtype_code(x), x.stride(0), rows, C, rb, N, coef, float(slope), out,
+                  _lib.dtype_code(out), out.stride(0))
+        ctx.save_for_backward(x, rb, coef)
+        ctx.training, ctx.slope, ctx.N = training, slope, N
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, rb, coef = ctx.saved_tensors
+        rows, C = x.shape
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        dgb = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+        dx = torch.empty(rows, C, dtype=x.dtype, device=x.device)
+        _lib.call("fs_bn_act_bwd", x, g, _lib.dtype_code(g), g.stride(0), x, _lib.dtype_code(x), x.stride(0), rows, C, rb,
+                  ctx.N, coef, float(ctx.slope), dgb, float(rows), int(ctx.training), dx, _lib.dtype_code(dx),
+                  dx.stride(0))
+        dgb32 = dgb.float()
+        drb = dx.view(-1, ctx.N, C).sum(dim=1, dtype=torch.float32) if rb is not None else None
+        return dx, drb, dgb32[C:], dgb32[:C], None, None, None, None, None, None, None, None
+
+
+def bn_act(x, bn, slope, rowbias=None, N=1):
+    """BatchNorm(+LeakyReLU) over the rows of x (rows, C); bn is the nn.BatchNorm module holding the state."""
+    assert x.stride(1) == 1
+    return _BnActFn.apply(x, rowbias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                          bn.training, bn.eps, bn.momentum, slope, N)
+
+
+class _PoolBnActFn(torch.autograd.Function):
+    """(B, C) = max over the N rows of each cloud of LeakyReLU(BatchNorm(x)) without writing the activation:
+    Conv1d + BN + LeakyReLU + AdaptiveMaxPool1d of the global feature (models/dgcnn.py:123-126, 156)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, training, eps, momentum, slope, B, N):
+        C = x.shape[1]
+        dev = x.device
+        gamma32, beta32 = gamma.detach().float(), beta.detach().float()
+        sel = torch.empty(B, C, dtype=torch.float32, device=dev)
+        arg = torch.empty(B, C, dtype=torch.int32, device=dev)
+        stats = torch.zeros(3 * C, dtype=torch.float64, device=dev) if training else None
+        _lib.call("fs_pool_reduce", x, x, _lib.dtype_code(x), x.stride(0), B, N, C, gamma32, sel, arg, stats)
+        coef = _bn_coef(x, stats, B * N, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
+        out = torch.empty(B, C, dtype=x.dtype, device=dev)
+        _lib.call("fs_bn_act_apply", x, sel, 0, C, B, C, None, 1, coef, float(slope), out, _lib.dtype_code(out), C)
+        ctx.save_for_backward(x, sel, arg, coef)
+        ctx.training, ctx.slope, ctx.B, ctx.N = training, slope, B, N
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, sel, arg, coef = ctx.saved_tensors
+        B, N, C = ctx.B, ctx.N, x.shape[1]
+        g32 = g.float().contiguous()
+        dgb = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+        _lib.call("fs_bn_act_bwd", x, g32, 0, C, sel, 0, C, B, C, None, 1, coef, float(ctx.slope), dgb, float(B * N),
+                  int(ctx.training), None, 0, C)
+        dx = torch.empty(B * N, C, dtype=x.dtype, device=x.device)
+        _lib.call("fs_pool_bwd", x, x, _lib.dtype_code(x), x.stride(0), B, N, C, g32, sel, arg, coef, float(ctx.slope), dgb,
+                  float(B * N), int(ctx.training), dx, _lib.dtype_code(dx), C)
+        dgb32 = dgb.float()
+        return dx, dgb32[C:], dgb32[:C], None, None, None, None, None, None, None, None, None
+
+
+def pool_bn_act(x, bn, slope, B, N):
+    assert x.stride(1) == 1
+    return _PoolBnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                              bn.training, bn.eps, bn.momentum, slope, B, N)

@@ -219,6 +219,42 @@ int fs_edge_reduce_bwd(int device, fs_stream_t stream, const void* z, int z_dtyp
                        const uint8_t* arg, long long P, int k, int Cp, const float* coef,
                        const double* dgb, double count, int train_stats, void* dz, int dz_dtype);
 
+/* ---------------------------------------------------------------- dense layers ------------- */
+
+/*
+ * BatchNorm + LeakyReLU around the 1x1-conv GEMMs of SharedFullyConnected(dim=1) (models/dgcnn.py:282-323,
+ * used at :123-137) on point-major tables x [rows, ld] (fp32 or bf16, C a power of two >= 64).
+ * `rowbias` (nullable) is a per-cloud bias [rows/N, C] fp32 added to x on load: segmentation[0] on
+ * [local | broadcast global] (models/dgcnn.py:159) = local GEMM + one bias row per cloud.
+ *   fs_colstats      stats [3*C] f64 += per-column sum(x-p), sum((x-p)^2); writes pivot p (zero stats first);
+ *                    feed fs_bn_finalize with count = rows.
+ *   fs_bn_act_apply  out = LeakyReLU_slope(scale*(x - mu) + beta)
+ *   fs_bn_act_bwd    dgb [2*C] f64 += (sum d, sum d*xhat) with d = g*LeakyReLU'(z); then (dx non-null)
+ *                    dx = scale*(d - dbeta/M - xhat*dgamma/M)   (train_stats = 0: dx = scale*d)
+ */
+int fs_colstats(int device, fs_stream_t stream, const void* x, int dtype, int ld, long long rows, int C,
+                const float* rowbias, int N, double* stats);
+int fs_bn_act_apply(int device, fs_stream_t stream, const void* x, int dtype, int ld, long long rows,
+                    int C, const float* rowbias, int N, const float* coef, float slope, void* out,
+                    int out_dtype, int ld_out);
+int fs_bn_act_bwd(int device, fs_stream_t stream, const void* g, int g_dtype, int ldg, const void* x,
+                  int dtype, int ld, long long rows, int C, const float* rowbias, int N, const float* coef,
+                  float slope, double* dgb, double count, int train_stats, void* dx, int dx_dtype,
+                  int ld_dx);
+
+/*
+ * Global max-pool fused with BatchNorm statistics (global_feature = Conv1d + BN + LeakyReLU +
+ * AdaptiveMaxPool1d, models/dgcnn.py:123-126, 156): LeakyReLU(BN(.)) is monotone, so only the per-cloud
+ * max (gamma >= 0) / min (gamma < 0) of the GEMM output x [B*N, ld] is needed.
+ *   fs_pool_reduce  sel [B,C] f32, arg [B,C] i32 (row within the cloud), stats as fs_colstats (nullable)
+ *   fs_pool_bwd     dX[r,c] = scale*([r==arg[b,c]]*g[b,c]*LeakyReLU'(z_sel) - dbeta/M - xhat*dgamma/M)
+ */
+int fs_pool_reduce(int device, fs_stream_t stream, const void* x, int dtype, int ld, int B, int N, int C,
+                   const float* gamma, float* sel, int32_t* arg, double* stats);
+int fs_pool_bwd(int device, fs_stream_t stream, const void* x, int dtype, int ld, int B, int N, int C,
+                const float* g, const float* sel, const int32_t* arg, const float* coef, float slope,
+                const double* dgb, double count, int train_stats, void* dx, int dx_dtype, int ld_dx);
+
 /* ---------------------------------------------------------------- Chamfer ------------------ */
 
 /*

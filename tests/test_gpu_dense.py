@@ -1,0 +1,78 @@
+"""BatchNorm+LeakyReLU and fused global max-pool kernels vs plain PyTorch fp32 (floating-point kernels:
+rtol 1e-4 / atol 1e-5 on outputs and gradients, rtol 1e-4 on running statistics)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from fissure_segmentation_b200 import ops
+from parity import assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bn(C, seed):
+    gen = torch.Generator().manual_seed(seed)
+    bn = torch.nn.BatchNorm1d(C)
+    with torch.no_grad():
+        bn.weight.copy_((0.5 + torch.rand(C, generator=gen)) * torch.where(torch.rand(C, generator=gen) < 0.3, -1.0, 1.0))
+        bn.bias.copy_(0.2 * torch.randn(C, generator=gen))
+        bn.running_mean.copy_(0.1 * torch.randn(C, generator=gen))
+        bn.running_var.copy_(0.5 + torch.rand(C, generator=gen))
+    return bn
+
+
+@pytest.mark.parametrize("rows,C,N,bias,training", [(4096, 256, 1024, True, True), (4096, 64, 1, False, True),
+                                                    (3000, 1024, 1, False, True), (2048, 128, 512, True, False)])
+def test_bn_act_matches_torch(lib, rows, C, N, bias, training):
+    gen = torch.Generator().manual_seed(rows + C)
+    x = (torch.randn(rows, C, generator=gen) * 2 + 0.7)
+    rb = torch.randn(rows // N, C, generator=gen) if bias else None
+    gout = torch.randn(rows, C, generator=gen)
+    bn_ref, bn_gpu = _bn(C, 3), _bn(C, 3).to(DEV)
+    bn_ref.train(training); bn_gpu.train(training)
+
+    xr = x.clone().requires_grad_(True)
+    rbr = rb.clone().requires_grad_(True) if bias else None
+    xin = xr if not bias else (xr.view(-1, N, C) + rbr.unsqueeze(1)).view(rows, C)
+    ref = F.leaky_relu(bn_ref(xin), 0.2)
+    ref.backward(gout)
+
+    xg = x.to(DEV).requires_grad_(True)
+    rbg = rb.to(DEV).requires_grad_(True) if bias else None
+    out = ops.bn_act(xg, bn_gpu, 0.2, rbg, N)
+    out.backward(gout.to(DEV))
+    assert_close(out, ref, 1e-4, 1e-5, "forward")
+    assert rel_err(xg.grad, xr.grad) < 1e-4
+    assert_close(xg.grad, xr.grad, 1e-3, 1e-4 * float(xr.grad.abs().max()), "dx")
+    assert rel_err(bn_gpu.weight.grad, bn_ref.weight.grad) < 1e-4
+    assert rel_err(bn_gpu.bias.grad, bn_ref.bias.grad) < 1e-4
+    if bias:
+        assert rel_err(rbg.grad, rbr.grad) < 1e-4
+    if training:
+        assert_close(bn_gpu.running_mean, bn_ref.running_mean, 1e-4, 1e-6, "running_mean")
+        assert_close(bn_gpu.running_var, bn_ref.running_var, 1e-4, 1e-6, "running_var")
+        assert int(bn_gpu.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("B,N,C,training,dtype", [(4, 1000, 1024, True, torch.float32), (2, 2048, 128, False, torch.float32),
+                                                  (3, 512, 1024, True, torch.bfloat16)])
+def test_pool_bn_act_matches_torch(lib, B, N, C, training, dtype):
+    gen = torch.Generator().manual_seed(B * N + C)
+    x = (torch.randn(B * N, C, generator=gen) * 1.5 - 0.3).to(dtype)
+    gout = torch.randn(B, C, generator=gen)
+    bn_ref, bn_gpu = _bn(C, 5), _bn(C, 5).to(DEV)
+    bn_ref.train(training); bn_gpu.train(training)
+    xr = x.float().clone().requires_grad_(True)
+    ref = F.leaky_relu(bn_ref(xr), 0.2).view(B, N, C).amax(dim=1)
+    ref.backward(gout)
+    xg = x.to(DEV).requires_grad_(True)
+    out = ops.pool_bn_act(xg, bn_gpu, 0.2, B, N)
+    out.float().backward(gout.to(DEV))
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert_close(out, ref, tol, tol, "pooled output")
+    assert rel_err(xg.grad, xr.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
+    assert rel_err(bn_gpu.weight.grad, bn_ref.weight.grad) < 1e-4
+    assert rel_err(bn_gpu.bias.grad, bn_ref.bias.grad) < 1e-4
+    if training:
+        assert_close(bn_gpu.running_var, bn_ref.running_var, 1e-4, 1e-6, "running_var")
