@@ -62,39 +62,51 @@ __device__ __forceinline__ void add_bias(float* f, const float* __restrict__ bia
     }
 }
 
-// Per-column sums of (x - pivot), (x - pivot)^2 in fp64; pivot = row 0. stats = [S1 | S2 | pivot], each C.
+// Per-column sums of (x - pivot), (x - pivot)^2 in fp64; pivot = row 0 (layout: fs_stats_commit in fs_common.cuh).
+// Requires C <= tpr * V, i.e. one channel vector per thread (C <= 1024 fp32, <= 2048 bf16).
 template <typename T>
 __global__ void __launch_bounds__(DN_THREADS)
 colstats_kernel(const T* __restrict__ x, int ld, long long rows, int C, const float* __restrict__ bias, int N,
                 double* __restrict__ stats) {
     constexpr int V = Vec<T>::N;
-    extern __shared__ double red[];     // [2*C]
+    extern __shared__ double red[];     // [2 * V * DN_THREADS]
     RowMap m(C, V);
-    for (int c = threadIdx.x; c < 2 * C; c += DN_THREADS) red[c] = 0.0;
-    __syncthreads();
-    for (int cc = m.c0; cc < C; cc += m.tpr * V) {
-        float piv[V];
-        Vec<T>::load(x + cc, piv);
-        add_bias<V>(piv, bias, 0, N, C, cc);
-        float s1[V], s2[V];
+    const int cc = m.c0;
+    float piv[V];
+    Vec<T>::load(x + cc, piv);
+    add_bias<V>(piv, bias, 0, N, C, cc);
+    float s1[V], s2[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-        for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += (long long)gridDim.x * m.rows_per_pass) {
-            float f[V];
-            Vec<T>::load(x + row * ld + cc, f);
-            add_bias<V>(f, bias, row, N, C, cc);
+    for (int i = 0; i < V; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+    const long long step = (long long)gridDim.x * m.rows_per_pass;
+    long long row = (long long)blockIdx.x * m.rows_per_pass + m.r;
+    for (; row + 3 * step < rows; row += 4 * step) {       // 4 independent 128-bit loads in flight per thread
+        float f[4][V];
 #pragma unroll
-            for (int i = 0; i < V; ++i) { const float d = f[i] - piv[i]; s1[i] += d; s2[i] = fmaf(d, d, s2[i]); }
-        }
+        for (int u = 0; u < 4; ++u) Vec<T>::load(x + (row + u * step) * ld + cc, f[u]);
 #pragma unroll
-        for (int i = 0; i < V; ++i) { atomicAdd(&red[cc + i], (double)s1[i]); atomicAdd(&red[C + cc + i], (double)s2[i]); }
-        if (blockIdx.x == 0 && m.r == 0) {
+        for (int u = 0; u < 4; ++u) {
+            add_bias<V>(f[u], bias, row + u * step, N, C, cc);
 #pragma unroll
-            for (int i = 0; i < V; ++i) stats[2 * C + cc + i] = (double)piv[i];
+            for (int i = 0; i < V; ++i) { const float d = f[u][i] - piv[i]; s1[i] += d; s2[i] = fmaf(d, d, s2[i]); }
         }
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < 2 * C; c += DN_THREADS) atomicAdd(&stats[c], red[c]);
+    for (; row < rows; row += step) {
+        float f[V];
+        Vec<T>::load(x + row * ld + cc, f);
+        add_bias<V>(f, bias, row, N, C, cc);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { const float d = f[i] - piv[i]; s1[i] += d; s2[i] = fmaf(d, d, s2[i]); }
+    }
+    double d1[V], d2[V];
+    int chans[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { d1[i] = (double)s1[i]; d2[i] = (double)s2[i]; chans[i] = cc + i; }
+    fs_stats_commit<V>(red, d1, d2, chans, m.tpr, C, stats);
+    if (blockIdx.x == 0 && m.r == 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) stats[2 * C + cc + i] = (double)piv[i];
+    }
 }
 
 // y = LeakyReLU(scale * (x - mu) + beta)
@@ -133,55 +145,57 @@ bn_act_apply_kernel(const T* __restrict__ x, int ld, long long rows, int C, cons
     }
 }
 
-// d = g * LeakyReLU'(z); dgb = [sum d | sum d * xhat] in fp64
+// d = g * LeakyReLU'(z); dgb = [sum d | sum d * xhat] in fp64 (layout: fs_stats_commit)
+__device__ __forceinline__ void load4_any(const float* p, float* f) { Vec<float>::load(p, f); }
+__device__ __forceinline__ void load4_any(const __nv_bfloat16* p, float* f) {
+    uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
+    f[0] = a.x; f[1] = a.y; f[2] = b2.x; f[3] = b2.y;
+}
+
 template <typename GT, typename T>
 __global__ void __launch_bounds__(DN_THREADS)
 bn_act_bwd_reduce_kernel(const GT* __restrict__ g, int ldg, const T* __restrict__ x, int ld, long long rows, int C,
                          const float* __restrict__ bias, int N, const float* __restrict__ coef, float slope,
                          double* __restrict__ dgb) {
     constexpr int V = 4;
-    extern __shared__ double red[];
+    extern __shared__ double red[];     // [2 * V * DN_THREADS]
     RowMap m(C, V);
-    for (int c = threadIdx.x; c < 2 * C; c += DN_THREADS) red[c] = 0.0;
-    __syncthreads();
-    for (int cc = m.c0; cc < C; cc += m.tpr * V) {
-        float mu[V], inv[V], sc[V], be[V], s1[V], s2[V];
+    const int cc = m.c0;
+    float mu[V], inv[V], sc[V], be[V], s1[V], s2[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            mu[i] = __ldg(coef + cc + i); inv[i] = __ldg(coef + C + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i);
-            be[i] = __ldg(coef + 3 * C + cc + i); s1[i] = 0.f; s2[i] = 0.f;
-        }
-        for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += (long long)gridDim.x * m.rows_per_pass) {
-            float gv[V], f[V];
-            if (sizeof(GT) == 4) Vec<float>::load(reinterpret_cast<const float*>(g) + row * ldg + cc, gv);
-            else {
-                uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g) + row * ldg + cc));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-                float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
-                gv[0] = a.x; gv[1] = a.y; gv[2] = b2.x; gv[3] = b2.y;
-            }
-            if (sizeof(T) == 4) Vec<float>::load(reinterpret_cast<const float*>(x) + row * ld + cc, f);
-            else {
-                uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + row * ld + cc));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-                float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
-                f[0] = a.x; f[1] = a.y; f[2] = b2.x; f[3] = b2.y;
-            }
-            add_bias<V>(f, bias, row, N, C, cc);
+    for (int i = 0; i < V; ++i) {
+        mu[i] = __ldg(coef + cc + i); inv[i] = __ldg(coef + C + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i);
+        be[i] = __ldg(coef + 3 * C + cc + i); s1[i] = 0.f; s2[i] = 0.f;
+    }
+    const long long step = (long long)gridDim.x * m.rows_per_pass;
+    long long row = (long long)blockIdx.x * m.rows_per_pass + m.r;
+    for (; row < rows; row += 2 * step) {
+        float gv[2][V], f[2][V];
+        const bool two = row + step < rows;
+        load4_any(g + row * ldg + cc, gv[0]);
+        load4_any(x + row * ld + cc, f[0]);
+        if (two) { load4_any(g + (row + step) * ldg + cc, gv[1]); load4_any(x + (row + step) * ld + cc, f[1]); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            add_bias<V>(f[u], bias, row + u * step, N, C, cc);
 #pragma unroll
             for (int i = 0; i < V; ++i) {
-                const float xc = f[i] - mu[i];
+                const float xc = f[u][i] - mu[i];
                 const float z = fmaf(sc[i], xc, be[i]);
-                const float d = z > 0.f ? gv[i] : slope * gv[i];
+                const float d = z > 0.f ? gv[u][i] : slope * gv[u][i];
                 s1[i] += d;
                 s2[i] = fmaf(d, xc * inv[i], s2[i]);
             }
         }
-#pragma unroll
-        for (int i = 0; i < V; ++i) { atomicAdd(&red[cc + i], (double)s1[i]); atomicAdd(&red[C + cc + i], (double)s2[i]); }
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < 2 * C; c += DN_THREADS) atomicAdd(&dgb[c], red[c]);
+    double d1[V], d2[V];
+    int chans[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { d1[i] = (double)s1[i]; d2[i] = (double)s2[i]; chans[i] = cc + i; }
+    fs_stats_commit<V>(red, d1, d2, chans, m.tpr, C, dgb);
 }
 
 // dx = scale * (d - dbeta/M - xhat * dgamma/M)      (train_stats = 0: dx = scale * d)
@@ -341,10 +355,10 @@ pool_bwd_kernel(const T* __restrict__ x, int ld, int N, long long rows, int C, c
 
 int dn_grid(long long rows, int rows_per_pass) {
     long long need = (rows + rows_per_pass - 1) / rows_per_pass;
-    const long long cap = (long long)FS_NUM_SMS * 8;
+    const long long cap = (long long)FS_NUM_SMS * 4;
     return (int)(need < 1 ? 1 : (need > cap ? cap : need));
 }
-bool pow2_width(int C, int vec) { return C >= 64 && C <= 4096 && (C & (C - 1)) == 0 && C % vec == 0; }
+bool pow2_width(int C, int vec) { return C >= 64 && C <= 1024 && (C & (C - 1)) == 0 && C % vec == 0; }
 int rows_per_pass(int C, int vec) { int tpr = C / vec; if (tpr > DN_THREADS) tpr = DN_THREADS; return DN_THREADS / tpr; }
 
 }  // namespace
@@ -357,7 +371,7 @@ extern "C" int fs_colstats(int device, fs_stream_t stream_, const void* x, int d
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int grid = dn_grid(rows, rows_per_pass(C, vec));
-    const size_t smem = (size_t)2 * C * sizeof(double);
+    const size_t smem = (size_t)2 * vec * DN_THREADS * sizeof(double);
     if (dtype == FS_BF16) colstats_kernel<<<grid, DN_THREADS, smem, stream>>>((const __nv_bfloat16*)x, ld, rows, C, rowbias, N, stats);
     else colstats_kernel<<<grid, DN_THREADS, smem, stream>>>((const float*)x, ld, rows, C, rowbias, N, stats);
     FS_RETURN_IF_LAUNCH_FAILED();
@@ -391,7 +405,7 @@ extern "C" int fs_bn_act_bwd(int device, fs_stream_t stream_, const void* g, int
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int grid = dn_grid(rows, rows_per_pass(C, 4));
-    const size_t smem = (size_t)2 * C * sizeof(double);
+    const size_t smem = (size_t)2 * 4 * DN_THREADS * sizeof(double);
 #define RED(GT, T) bn_act_bwd_reduce_kernel<<<grid, DN_THREADS, smem, stream>>>((const GT*)g, ldg, (const T*)x, ld, rows, C, rowbias, N, coef, slope, dgb)
     if (g_dtype == FS_BF16 && dtype == FS_BF16) RED(__nv_bfloat16, __nv_bfloat16);
     else if (g_dtype == FS_BF16) RED(__nv_bfloat16, float);

@@ -45,21 +45,6 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float* f) {
     *reinterpret_cast<uint2*>(p) = v;
 }
 
-// Block-level accumulation of per-thread per-channel double partials into global memory.
-// red: shared double[2*CP]; each thread owns NCH channels starting at chan(l, v).
-template <int CP>
-__device__ __forceinline__ void block_channel_reduce(double* red, const double* s1, const double* s2,
-                                                     const int* chans, int nch, double* gout) {
-    for (int c = threadIdx.x; c < 2 * CP; c += blockDim.x) red[c] = 0.0;
-    __syncthreads();
-    for (int e = 0; e < nch; ++e) {
-        atomicAdd(&red[chans[e]], s1[e]);
-        atomicAdd(&red[CP + chans[e]], s2[e]);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < 2 * CP; c += blockDim.x) atomicAdd(&gout[c], red[c]);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Pass 1 (train) / single pass (eval): gather the k neighbour rows of a, select max/min.
 // MODE 0: train gather  -> sel, arg, sy, stats
@@ -73,7 +58,7 @@ edgeconv_gather_kernel(const TT* __restrict__ table, int ld, const int32_t* __re
                        OT* __restrict__ out, int ld_out) {
     using M = EcMap<TT, CP>;
     constexpr int VEC = M::VEC, NV = M::NV, NCH = M::NCH;
-    __shared__ double red[2 * CP];
+    __shared__ double red[MODE == 0 ? 2 * NCH * EC_THREADS : 1];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -200,7 +185,7 @@ edgeconv_gather_kernel(const TT* __restrict__ table, int ld, const int32_t* __re
         }
     }
     if (MODE == 0 && stats) {
-        block_channel_reduce<CP>(red, s1, s2, chans, NCH, stats);
+        fs_stats_commit<NCH>(red, s1, s2, chans, M::LPP, CP, stats);
         if (blockIdx.x == 0) {
             __syncthreads();
             if (warp == 0 && sub == 0) {
@@ -350,7 +335,7 @@ edgeconv_bwd_reduce_kernel(const GT* __restrict__ g, int ldg, const float* __res
     constexpr int Q = CP / 4;              // threads per point row
     constexpr int ROWS = 256 / Q;          // rows per block pass
     static_assert(256 % Q == 0, "CP must divide 1024");
-    __shared__ double red[2 * CP];
+    __shared__ double red[2 * 4 * 256];
     const int l = threadIdx.x % Q;
     const int r = threadIdx.x / Q;
     const int c0 = l * 4;
@@ -378,7 +363,7 @@ edgeconv_bwd_reduce_kernel(const GT* __restrict__ g, int ldg, const float* __res
         store4(d + pt * CP + c0, dv);
     }
     int chans[4] = {c0, c0 + 1, c0 + 2, c0 + 3};
-    block_channel_reduce<CP>(red, s1, s2, chans, 4, dgb);
+    fs_stats_commit<4>(red, s1, s2, chans, Q, CP, dgb);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -539,7 +524,7 @@ edge_reduce_kernel(const ZT* __restrict__ z, long long P, int k, const float* __
                    float* __restrict__ sel, uint8_t* __restrict__ arg, float* __restrict__ sy, double* __restrict__ stats) {
     constexpr int Q = CP / 4;
     constexpr int ROWS = 256 / Q;
-    __shared__ double red[2 * CP];
+    __shared__ double red[2 * 4 * 256];
     const int l = threadIdx.x % Q;
     const int r = threadIdx.x / Q;
     const int c0 = l * 4;
@@ -579,7 +564,7 @@ edge_reduce_kernel(const ZT* __restrict__ z, long long P, int k, const float* __
     }
     if (stats) {
         int chans[4] = {c0, c0 + 1, c0 + 2, c0 + 3};
-        block_channel_reduce<CP>(red, s1, s2, chans, 4, stats);
+        fs_stats_commit<4>(red, s1, s2, chans, Q, CP, stats);
         if (blockIdx.x == 0 && r == 0) {
             __syncthreads();
 #pragma unroll

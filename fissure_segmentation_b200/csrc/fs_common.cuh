@@ -107,3 +107,54 @@ __device__ __forceinline__ float fs_warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FS_FULL_MASK, v, o);
     return v;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Per-channel statistics buffers (fp64). Layout, C channels, S = fs_stat_slots(C):
+//   [0, 2C)  final sums (sum1 | sum2)     [2C, 3C)  pivot     [3C, 3C + S*2C)  slot partials     [+0]  ticket
+// Blocks add their partials into slot (blockIdx.x % S) (S-fold less contention than one set of addresses);
+// the last block to finish sums the slots into the final area. The caller zero-fills the buffer.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int fs_stat_slots(int C) {
+    int s = 2048 / C;
+    return s < 1 ? 1 : (s > 32 ? 32 : s);
+}
+__host__ __device__ inline long long fs_stats_doubles(int C) { return 3ll * C + (long long)fs_stat_slots(C) * 2 * C + 2; }
+
+// Threads whose (threadIdx.x % period) agree own the same NCH channels chan[0..NCH).
+// buf: shared double[2 * NCH * blockDim.x]. Every thread of the block must call this exactly once per kernel.
+template <int NCH>
+__device__ __forceinline__ void fs_stats_commit(double* buf, const double* s1, const double* s2, const int* chan,
+                                                int period, int C, double* gstats) {
+    const int T = blockDim.x, t = threadIdx.x;
+    __shared__ bool fs_last_block;
+#pragma unroll
+    for (int e = 0; e < NCH; ++e) {
+        buf[e * T + t] = s1[e];
+        buf[(NCH + e) * T + t] = s2[e];
+    }
+    __syncthreads();
+    const int slots = fs_stat_slots(C);
+    double* slot = gstats + 3 * C + (blockIdx.x % slots) * 2 * C;
+    if (t < period) {
+#pragma unroll
+        for (int e = 0; e < NCH; ++e) {
+            double a = 0.0, b = 0.0;
+            for (int j = t; j < T; j += period) { a += buf[e * T + j]; b += buf[(NCH + e) * T + j]; }
+            atomicAdd(slot + chan[e], a);
+            atomicAdd(slot + C + chan[e], b);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    unsigned* ticket = reinterpret_cast<unsigned*>(gstats + 3 * C + slots * 2 * C);
+    if (t == 0) fs_last_block = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (fs_last_block) {
+        __threadfence();
+        for (int c = t; c < 2 * C; c += T) {
+            double a = 0.0;
+            for (int sidx = 0; sidx < slots; ++sidx) a += __ldcg(gstats + 3 * C + sidx * 2 * C + c);
+            gstats[c] = a;
+        }
+    }
+}

@@ -183,7 +183,9 @@ int flat_grid(long long total) {
 
 }  // namespace
 
-extern "C" int fs_version(void) { return 100; }
+extern "C" int fs_version(void) { return 101; }
+
+extern "C" size_t fs_stats_buffer_doubles(int C) { return C > 0 ? (size_t)fs_stats_doubles(C) : 0; }
 
 extern "C" const char* fs_error_string(int code) {
     switch (code) {

@@ -106,6 +106,11 @@ def knn_any(x, k, self_loop=False, diag_zero=True, return_dist=False):
 
 # ------------------------------------------------------------------------------------------- EdgeConv
 
+def _stats_buffer(C, device):
+    """Zero-filled fp64 statistics buffer (final sums | pivot | slot partials | ticket) for C channels."""
+    return torch.zeros(_lib.load().fs_stats_buffer_doubles(C), dtype=torch.float64, device=device)
+
+
 def _bn_coef(table_ref, stats, count, gamma, beta, running_mean, running_var, nbt, training, Cp, eps, momentum):
     coef = torch.empty(4 * Cp, dtype=torch.float32, device=table_ref.device)
     if training:
@@ -132,7 +137,7 @@ class _EdgeConvFn(torch.autograd.Function):
         arg = torch.empty(P, Cp, dtype=torch.uint8, device=dev)
         need_grad = any(ctx.needs_input_grad[:3])
         sy = torch.empty(P, Cp, dtype=torch.float32, device=dev) if (training and need_grad) else None
-        stats = torch.zeros(3 * Cp, dtype=torch.float64, device=dev) if training else None
+        stats = _stats_buffer(Cp, dev) if training else None
         _lib.call("fs_edgeconv_gather", table, table, dt, table.stride(0), idx, B, N, k, Cp, gamma32, sel, arg, sy,
                   stats)
         coef = _bn_coef(table, stats, P * k, gamma32, beta32, running_mean, running_var, nbt, training, Cp, eps,
@@ -158,7 +163,7 @@ class _EdgeConvFn(torch.autograd.Function):
         if g.stride(1) != 1:
             g = g.contiguous()
         d = torch.empty(P, Cp, dtype=torch.float32, device=dev)
-        dgb = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+        dgb = _stats_buffer(Cp, dev)
         _lib.call("fs_edgeconv_bwd_reduce", table, g, _lib.dtype_code(g), g.stride(0), sel, table, dt, table.stride(0),
                   P, Cp, coef, d, dgb)
         dT = torch.empty(P, 2 * Cp, dtype=torch.float32, device=dev)
@@ -235,7 +240,7 @@ class _EdgeReduceFn(torch.autograd.Function):
         gamma32, beta32 = gamma.detach().float(), beta.detach().float()
         sel = torch.empty(P, Cp, dtype=torch.float32, device=dev)
         arg = torch.empty(P, Cp, dtype=torch.uint8, device=dev)
-        stats = torch.zeros(3 * Cp, dtype=torch.float64, device=dev) if training else None
+        stats = _stats_buffer(Cp, dev) if training else None
         _lib.call("fs_edge_reduce", z, z, _lib.dtype_code(z), P, k, Cp, gamma32, sel, arg, None, stats)
         coef = _bn_coef(z, stats, P * k, gamma32, beta32, running_mean, running_var, nbt, training, Cp, eps, momentum)
         out = torch.empty(P, Cp, dtype=z.dtype, device=dev)
@@ -256,12 +261,12 @@ class _EdgeReduceFn(torch.autograd.Function):
         if g.stride(1) != 1:
             g = g.contiguous()
         d = torch.empty(P, Cp, dtype=torch.float32, device=dev)
-        dgb = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+        dgb = _stats_buffer(Cp, dev)
         _lib.call("fs_edgeconv_bwd_reduce", z, g, _lib.dtype_code(g), g.stride(0), sel, None, 0, 0, P, Cp, coef, d, dgb)
         dz = torch.empty_like(z)
         _lib.call("fs_edge_reduce_bwd", z, z, _lib.dtype_code(z), d, arg, P, k, Cp, coef, dgb, float(P * k),
                   int(ctx.training), dz, _lib.dtype_code(dz))
-        dgb32 = dgb.float()
+        dgb32 = dgb[:2 * Cp].float()
         return dz, dgb32[Cp:], dgb32[:Cp], None, None, None, None, None, None, None
 
 
@@ -320,16 +325,6 @@ def nn_points(x, y):
 
 # ------------------------------------------------------------------------------------------- dense layers
 
-def _col_bn_coef(x, rows, C, rowbias, N, gamma32, beta32, bn, training):
-    """Batch statistics of the columns of x (train) or running statistics (eval) -> coef [mu|invstd|scale|beta]."""
-    if training:
-        stats = torch.zeros(3 * C, dtype=torch.float64, device=x.device)
-        _lib.call("fs_colstats", x, x, _lib.dtype_code(x), x.stride(0), rows, C, rowbias, N, stats)
-    else:
-        stats = None
-    return stats
-
-
 class _BnActFn(torch.autograd.Function):
     """y = LeakyReLU(BatchNorm(x + rowbias[cloud])) on a point-major table (SharedFullyConnected, dim=1:
     models/dgcnn.py:306-315 after the 1x1 conv). Statistics over all rows, fp64 accumulation."""
@@ -341,7 +336,7 @@ class _BnActFn(torch.autograd.Function):
         rb = rowbias.detach().float().contiguous() if rowbias is not None else None
         stats = None
         if training:
-            stats = torch.zeros(3 * C, dtype=torch.float64, device=x.device)
+            stats = _stats_buffer(C, x.device)
             _lib.call("fs_colstats", x, x, _lib.dtype_code(x), x.stride(0), rows, C, rb, N, stats)
         coef = _bn_coef(x, stats, rows, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
         out = torch.empty(rows, C, dtype=x.dtype, device=x.device)
@@ -359,12 +354,12 @@ class _BnActFn(torch.autograd.Function):
             g = g.float()
         if g.stride(1) != 1:
             g = g.contiguous()
-        dgb = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+        dgb = _stats_buffer(C, x.device)
         dx = torch.empty(rows, C, dtype=x.dtype, device=x.device)
         _lib.call("fs_bn_act_bwd", x, g, _lib.dtype_code(g), g.stride(0), x, _lib.dtype_code(x), x.stride(0), rows, C, rb,
                   ctx.N, coef, float(ctx.slope), dgb, float(rows), int(ctx.training), dx, _lib.dtype_code(dx),
                   dx.stride(0))
-        dgb32 = dgb.float()
+        dgb32 = dgb[:2 * C].float()
         drb = dx.view(-1, ctx.N, C).sum(dim=1, dtype=torch.float32) if rb is not None else None
         return dx, drb, dgb32[C:], dgb32[:C], None, None, None, None, None, None, None, None
 
@@ -387,7 +382,7 @@ class _PoolBnActFn(torch.autograd.Function):
         gamma32, beta32 = gamma.detach().float(), beta.detach().float()
         sel = torch.empty(B, C, dtype=torch.float32, device=dev)
         arg = torch.empty(B, C, dtype=torch.int32, device=dev)
-        stats = torch.zeros(3 * C, dtype=torch.float64, device=dev) if training else None
+        stats = _stats_buffer(C, dev) if training else None
         _lib.call("fs_pool_reduce", x, x, _lib.dtype_code(x), x.stride(0), B, N, C, gamma32, sel, arg, stats)
         coef = _bn_coef(x, stats, B * N, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
         out = torch.empty(B, C, dtype=x.dtype, device=dev)
@@ -401,13 +396,13 @@ class _PoolBnActFn(torch.autograd.Function):
         x, sel, arg, coef = ctx.saved_tensors
         B, N, C = ctx.B, ctx.N, x.shape[1]
         g32 = g.float().contiguous()
-        dgb = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+        dgb = _stats_buffer(C, x.device)
         _lib.call("fs_bn_act_bwd", x, g32, 0, C, sel, 0, C, B, C, None, 1, coef, float(ctx.slope), dgb, float(B * N),
                   int(ctx.training), None, 0, C)
         dx = torch.empty(B * N, C, dtype=x.dtype, device=x.device)
         _lib.call("fs_pool_bwd", x, x, _lib.dtype_code(x), x.stride(0), B, N, C, g32, sel, arg, coef, float(ctx.slope), dgb,
                   float(B * N), int(ctx.training), dx, _lib.dtype_code(dx), C)
-        dgb32 = dgb.float()
+        dgb32 = dgb[:2 * C].float()
         return dx, dgb32[C:], dgb32[:C], None, None, None, None, None, None, None, None, None
 
 

@@ -40,6 +40,11 @@ enum fs_dtype { FS_F32 = 0, FS_BF16 = 1 };
 #define FS_MAX_K 127 /* largest k (k+1 when the self match is dropped must be <= 128) */
 
 int fs_version(void);
+/*
+ * Number of doubles of a per-channel statistics buffer for C channels (the `stats` / `dgb` arguments below):
+ * [0,2C) final sums | [2C,3C) pivot | slot partials | ticket. The caller zero-fills it before each use.
+ */
+size_t fs_stats_buffer_doubles(int C);
 /* Static string for a negative fs_status; cudaGetErrorString for positive codes. */
 const char* fs_error_string(int code);
 
@@ -114,9 +119,8 @@ int fs_furthestsampling(int device, fs_stream_t stream, int b, const float* xyz,
  *   sel [P,Cp]  f32   max_j a_j where gamma >= 0, min_j a_j where gamma < 0
  *   arg [P,Cp]  u8    slot (0..k-1) of the selected neighbour
  *   sy  [P,Cp]  f32   sum_j y(i,j)                      (nullable: eval / no-grad)
- *   stats [2*Cp+Cp] f64  sum(y-p), sum((y-p)^2) per channel (accumulated with atomics; must be
- *                     zeroed by the caller) followed by the pivot p (written by the kernel)
- *                     (nullable: eval mode, no batch statistics)
+ *   stats f64 [fs_stats_buffer_doubles(Cp)], zeroed by the caller: sum(y-p), sum((y-p)^2) per channel,
+ *                     then the pivot p (nullable: eval mode, no batch statistics)
  */
 int fs_edgeconv_gather(int device, fs_stream_t stream, const void* table, int dtype, int ld,
                        const int32_t* idx, int B, int N, int k, int Cp, const float* gamma,

@@ -64,7 +64,8 @@ def test_pool_bn_act_matches_torch(lib, B, N, C, training, dtype):
     bn_ref, bn_gpu = _bn(C, 5), _bn(C, 5).to(DEV)
     bn_ref.train(training); bn_gpu.train(training)
     xr = x.float().clone().requires_grad_(True)
-    ref = F.leaky_relu(bn_ref(xr), 0.2).view(B, N, C).amax(dim=1)
+    # AdaptiveMaxPool1d like the reference (models/dgcnn.py:125): one arg-max per (cloud, channel), first index on ties
+    ref = F.adaptive_max_pool1d(F.leaky_relu(bn_ref(xr), 0.2).view(B, N, C).transpose(1, 2), 1).squeeze(-1)
     ref.backward(gout)
     xg = x.to(DEV).requires_grad_(True)
     out = ops.pool_bn_act(xg, bn_gpu, 0.2, B, N)
