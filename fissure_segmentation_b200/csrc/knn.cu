@@ -91,6 +91,126 @@ knn3d_batch_kernel(const float* __restrict__ coords, long long batch_stride, lon
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Batched 3-D kNN, register-resident variant for clouds of up to 32*NPL points (N <= 2048).
+// One warp per query, lane l owns candidates j = i*32 + l and keeps ALL its NPL distances in registers.
+//   sweep    : distances + running minimum of CPL interleaved classes per lane (one FMNMX per candidate,
+//              no ballot, no branch);
+//   bound    : tau = kk-th smallest of the 32*CPL class minima — kk distinct candidates lie below it, so it
+//              bounds the kk-th smallest distance; its expected rank is M ln(M/(M-kk)), M = 32*CPL;
+//   collect  : lanes append their few entries <= tau to a shared queue (about 1.2 kk entries);
+//   select   : the warp-select of warp_select.cuh orders the survivors by (distance, index).
+// Same total order as the streaming kernel, hence the same result. A query whose survivors overflow the
+// queue falls back to streaming selection over the staged cloud.
+// ---------------------------------------------------------------------------------------------
+constexpr int KNN3R_WARPS = 8;
+constexpr int KNN3R_THREADS = KNN3R_WARPS * 32;
+constexpr int KNN3R_QPW = 4;                                  // queries per warp (sequential)
+constexpr int KNN3R_TILE_Q = KNN3R_WARPS * KNN3R_QPW;
+
+template <int NPL, int CPL, int KPL>
+__global__ void __launch_bounds__(KNN3R_THREADS, 2)
+knn3d_regs_kernel(const float* __restrict__ coords, long long batch_stride, long long chan_stride,
+                  long long point_stride, int N, int k, int self_loop, int diag_zero,
+                  int32_t* __restrict__ idx, float* __restrict__ dist2) {
+    constexpr int CAP = 32 * CPL * 2;                         // survivor queue entries per warp
+    extern __shared__ float smem[];
+    const int chunk = NPL * 32;
+    float* sx = smem;
+    float* sy = sx + chunk;
+    float* sz = sy + chunk;
+    float* sn = sz + chunk;
+    float* qd_all = sn + chunk;                               // [warps][64] warp-select queue
+    int* qi_all = reinterpret_cast<int*>(qd_all + KNN3R_WARPS * 64);
+    float* hd_all = reinterpret_cast<float*>(qi_all + KNN3R_WARPS * 64);   // [warps][CAP] survivors
+    int* hi_all = reinterpret_cast<int*>(hd_all + KNN3R_WARPS * CAP);
+    int* hn_all = hi_all + KNN3R_WARPS * CAP;                 // [warps] survivor counters
+
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const float* cb = coords + (long long)b * batch_stride;
+    const int kk = k + (self_loop ? 0 : 1);
+
+    for (int j = threadIdx.x; j < chunk; j += KNN3R_THREADS) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (j < N) {
+            const long long o = (long long)j * point_stride;
+            x = __ldg(cb + o); y = __ldg(cb + chan_stride + o); z = __ldg(cb + 2 * chan_stride + o);
+        }
+        sx[j] = x; sy[j] = y; sz[j] = z; sn[j] = sqnorm3(x, y, z);
+    }
+    __syncthreads();
+
+    float* hd = hd_all + warp * CAP;
+    int* hi = hi_all + warp * CAP;
+    int* hn = hn_all + warp;
+    FsWarpSelect<KPL> sel;
+
+    for (int r = 0; r < KNN3R_QPW; ++r) {
+        const int q = blockIdx.x * KNN3R_TILE_Q + r * KNN3R_WARPS + warp;
+        if (q >= N) break;                                    // warp-uniform
+        const float qx = sx[q], qy = sy[q], qz = sz[q], qq = sn[q];
+        float dist[NPL];
+        float cm[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) cm[c] = INFINITY;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const int j = i * 32 + lane;
+            const float dot = fmaf(qz, sz[j], fmaf(qy, sy[j], __fmul_rn(qx, sx[j])));
+            float d = diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * dot), sn[j]) : __fadd_rn(__fsub_rn(sn[j], 2.0f * dot), qq);
+            if (diag_zero && j == q) d = 0.f;
+            if (j >= N) d = INFINITY;
+            dist[i] = d;
+            cm[i % CPL] = fminf(cm[i % CPL], d);
+        }
+        // tau = kk-th smallest class minimum
+        sel.init(qd_all + warp * 64, qi_all + warp * 64, kk);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) sel.offer(cm[c], c * 32 + lane, true);
+        sel.finish();
+        float tau; int tj;
+        sel.get(kk - 1, tau, tj);
+        // collect survivors
+        if (lane == 0) *hn = 0;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            if (dist[i] <= tau) {
+                const int pos = atomicAdd(hn, 1);
+                if (pos < CAP) { hd[pos] = dist[i]; hi[pos] = i * 32 + lane; }
+            }
+        }
+        __syncwarp();
+        const int n = *hn;
+        sel.init(qd_all + warp * 64, qi_all + warp * 64, kk);
+        if (n <= CAP && tau < INFINITY) {
+            for (int base = 0; base < n; base += 32) {
+                const int s = base + lane;
+                const bool valid = s < n;
+                sel.offer(valid ? hd[s] : INFINITY, valid ? hi[s] : FS_IDX_PAD, valid);
+            }
+        } else {
+            // overflow (heavy ties) or fewer than kk finite distances: stream every candidate
+            // (distances recomputed from the staged cloud: a dynamic loop must not index the register array)
+#pragma unroll 1
+            for (int i = 0; i < NPL; ++i) {
+                const int j = i * 32 + lane;
+                const float dot = fmaf(qz, sz[j], fmaf(qy, sy[j], __fmul_rn(qx, sx[j])));
+                float d = diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * dot), sn[j]) : __fadd_rn(__fsub_rn(sn[j], 2.0f * dot), qq);
+                if (diag_zero && j == q) d = 0.f;
+                sel.offer(d, j, j < N);
+            }
+        }
+        sel.finish();
+        const long long row = ((long long)b * N + q) * k;
+        sel.store(self_loop ? 0 : 1, idx + row, dist2 ? dist2 + row : nullptr, 0, 0, INFINITY);
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Offset-segmented kNN (pointops knnquery): one warp per query, candidates read through L1.
 // ---------------------------------------------------------------------------------------------
@@ -266,6 +386,27 @@ extern "C" int fs_knn3d(int device, fs_stream_t stream_, const float* coords, lo
     if (kk > N || kk > FS_MAX_K + 1) return FS_ERR_BAD_ARG;
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (N <= 2048 && kk <= 64) {
+        // register-resident variant: every lane keeps its N/32 distances
+        dim3 rgrid(fs_div_up(N, KNN3R_TILE_Q), B);
+#define LAUNCH3R(NPL, CPL, KPL)                                                                                  \
+    do {                                                                                                         \
+        const size_t rs = (size_t)(NPL) * 32 * 4 * sizeof(float) + KNN3R_WARPS * 64 * 8 +                        \
+                          (size_t)KNN3R_WARPS * (32 * (CPL) * 2) * 8 + KNN3R_WARPS * sizeof(int);                \
+        int e = set_smem(knn3d_regs_kernel<NPL, CPL, KPL>, rs);                                                  \
+        if (e) return e;                                                                                         \
+        knn3d_regs_kernel<NPL, CPL, KPL><<<rgrid, KNN3R_THREADS, rs, stream>>>(                                  \
+            coords, batch_stride, chan_stride, point_stride, N, k, self_loop, diag_zero, idx, dist2);            \
+    } while (0)
+        if (kk <= 32) {
+            if (N <= 1024) LAUNCH3R(32, 2, 1); else LAUNCH3R(64, 2, 1);
+        } else {
+            if (N <= 1024) LAUNCH3R(32, 4, 2); else LAUNCH3R(64, 4, 2);
+        }
+#undef LAUNCH3R
+        FS_RETURN_IF_LAUNCH_FAILED();
+        return FS_OK;
+    }
     const int chunk = N < KNN3D_MAX_CHUNK ? ((N + 31) / 32) * 32 : KNN3D_MAX_CHUNK;
     const size_t smem = (size_t)chunk * 4 * sizeof(float) + KNN_WARPS * 64 * 8;
     dim3 grid(fs_div_up(N, KNN3D_TILE_Q), B);

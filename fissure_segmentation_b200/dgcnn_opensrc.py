@@ -49,7 +49,7 @@ def edgeconv_stage(x_pm, B, N, k, conv, graph, cdt):
     C = x_pm.shape[1]
     w = conv2d.weight.view(conv2d.out_channels, 2 * C)
     w_cat = torch.cat([w[:, :C], w[:, C:] - w[:, :C]], dim=0)
-    table = x_pm.float() @ w_cat.float().t()      # fp32 table in every mode (see dgcnn.EdgeConv.forward_pm)
+    table = ops.table_gemm(x_pm.float().contiguous(), w_cat.float())   # fp32 table in every mode (see dgcnn.EdgeConv.forward_pm)
     return ops.edgeconv_fused(table, bn.weight, bn.bias, graph, bn.running_mean, bn.running_var,
                               bn.num_batches_tracked, bn.training, eps=bn.eps, momentum=bn.momentum)
 

@@ -410,3 +410,37 @@ def pool_bn_act(x, bn, slope, B, N):
     assert x.stride(1) == 1
     return _PoolBnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
                               bn.training, bn.eps, bn.momentum, slope, B, N)
+
+
+# ------------------------------------------------------------------------------------------- per-point GEMM
+
+class _TableGemmFn(torch.autograd.Function):
+    """T = X W^T for a tall-skinny X (P x C, P ~ 1e5) and a small W (2Cp x C). The weight gradient
+    dW = dT^T X has a P-long reduction dimension and a tiny output; as one GEMM it runs on a few dozen CTAs,
+    so it is issued as a batched GEMM over row chunks followed by a sum over the chunks."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return x @ w.t()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = g @ w
+        if ctx.needs_input_grad[1]:
+            P = x.shape[0]
+            S = 1
+            while S < 128 and P % (2 * S) == 0 and P // (2 * S) >= 256:
+                S *= 2
+            if S > 1 and g.is_contiguous() and x.is_contiguous():
+                gw = torch.bmm(g.view(S, P // S, -1).transpose(1, 2), x.view(S, P // S, -1)).sum(dim=0)
+            else:
+                gw = g.t() @ x
+        return gx, gw
+
+
+def table_gemm(x, w):
+    return _TableGemmFn.apply(x, w)

@@ -72,8 +72,9 @@ def test_pool_bn_act_matches_torch(lib, B, N, C, training, dtype):
     out.float().backward(gout.to(DEV))
     tol = 1e-4 if dtype == torch.float32 else 1e-2
     assert_close(out, ref, tol, tol, "pooled output")
-    assert rel_err(xg.grad, xr.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
-    assert rel_err(bn_gpu.weight.grad, bn_ref.weight.grad) < 1e-4
-    assert rel_err(bn_gpu.bias.grad, bn_ref.bias.grad) < 1e-4
+    gtol = 1e-4 if dtype == torch.float32 else 1e-2     # bf16 output => the incoming gradient is bf16-rounded
+    assert rel_err(xg.grad, xr.grad) < gtol
+    assert rel_err(bn_gpu.weight.grad, bn_ref.weight.grad) < gtol
+    assert rel_err(bn_gpu.bias.grad, bn_ref.bias.grad) < gtol
     if training:
         assert_close(bn_gpu.running_var, bn_ref.running_var, 1e-4, 1e-6, "running_var")
