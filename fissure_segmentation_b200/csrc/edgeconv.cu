@@ -49,13 +49,22 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float* f) {
 // Pass 1 (train) / single pass (eval): gather the k neighbour rows of a, select max/min.
 // MODE 0: train gather  -> sel, arg, sy, stats
 // MODE 1: eval fused    -> out (= LeakyReLU(scale*(sel+b-mu)+beta)), optional arg
+//
+// Per edge and channel the loop does four instructions: S1 += a_j, compare, select value, select slot.
+// The batch statistics of y = a_j + b_i over all edges are NOT accumulated per edge; with the in-degree of
+// every point (reverse graph) they follow from per-point quantities, all shifted by pivots pa, pb (row 0):
+//     sum_e y'   = sum_i ( S1'_i + k b'_i )                         y' = y - (pa + pb), a' = a - pa, b' = b - pb
+//     sum_e y'^2 = sum_i ( indeg_i a'_i^2 + k b'_i^2 + 2 b'_i S1'_i )   S1'_i = sum_{j in N(i)} a'_j
+// evaluated in fp64 per point and channel (a_j ~ -b_i cancels, so the products must not round in fp32).
+// Each CTA owns a contiguous range of points: with spatially sorted clouds the neighbour rows of
+// consecutive points overlap and are served by L1.
 // ---------------------------------------------------------------------------------------------
 template <typename TT, int CP, int MODE, typename OT>
 __global__ void __launch_bounds__(EC_THREADS)
 edgeconv_gather_kernel(const TT* __restrict__ table, int ld, const int32_t* __restrict__ idx, long long P,
-                       int N, int k, const float* __restrict__ gamma_or_coef, float* __restrict__ sel_out,
-                       uint8_t* __restrict__ arg_out, float* __restrict__ sy_out, double* __restrict__ stats,
-                       OT* __restrict__ out, int ld_out) {
+                       int N, int k, const float* __restrict__ gamma_or_coef, const int32_t* __restrict__ rev_ptr,
+                       float* __restrict__ sel_out, uint8_t* __restrict__ arg_out, float* __restrict__ sy_out,
+                       double* __restrict__ stats, OT* __restrict__ out, int ld_out) {
     using M = EcMap<TT, CP>;
     constexpr int VEC = M::VEC, NV = M::NV, NCH = M::NCH;
     __shared__ double red[MODE == 0 ? 2 * NCH * EC_THREADS : 1];
@@ -65,8 +74,8 @@ edgeconv_gather_kernel(const TT* __restrict__ table, int ld, const int32_t* __re
     const int sub = lane / M::LPP;
     const int l = lane - sub * M::LPP;
 
-    bool use_max[NCH];
-    float pivot[NCH];
+    uint32_t flip[NCH];      // 0x80000000 where the minimum is wanted (gamma < 0): -a is maximised instead
+    float pa[NCH], pb[NCH];
     float mu[NCH], scale[NCH], beta[NCH];
     int chans[NCH];
 #pragma unroll
@@ -77,23 +86,20 @@ edgeconv_gather_kernel(const TT* __restrict__ table, int ld, const int32_t* __re
             const int c = c0 + e;
             chans[v * VEC + e] = c;
             if (MODE == 0) {
-                use_max[v * VEC + e] = __ldg(gamma_or_coef + c) >= 0.f;
+                flip[v * VEC + e] = __ldg(gamma_or_coef + c) >= 0.f ? 0u : 0x80000000u;
             } else {
                 mu[v * VEC + e] = __ldg(gamma_or_coef + c);
                 scale[v * VEC + e] = __ldg(gamma_or_coef + 2 * CP + c);
                 beta[v * VEC + e] = __ldg(gamma_or_coef + 3 * CP + c);
-                use_max[v * VEC + e] = scale[v * VEC + e] >= 0.f;
+                flip[v * VEC + e] = scale[v * VEC + e] >= 0.f ? 0u : 0x80000000u;
             }
         }
         if (MODE == 0 && stats) {
-            float fa[VEC], fb[VEC];
-            FsRow<TT>::load(table + c0, fa);
-            FsRow<TT>::load(table + CP + c0, fb);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) pivot[v * VEC + e] = fa[e] + fb[e];
+            FsRow<TT>::load(table + c0, pa + v * VEC);
+            FsRow<TT>::load(table + CP + c0, pb + v * VEC);
         } else {
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) pivot[v * VEC + e] = 0.f;
+            for (int e = 0; e < VEC; ++e) { pa[v * VEC + e] = 0.f; pb[v * VEC + e] = 0.f; }
         }
     }
     (void)mu; (void)scale; (void)beta;
@@ -102,64 +108,87 @@ edgeconv_gather_kernel(const TT* __restrict__ table, int ld, const int32_t* __re
 #pragma unroll
     for (int e = 0; e < NCH; ++e) { s1[e] = 0.0; s2[e] = 0.0; }
 
-    const long long stride = (long long)gridDim.x * EC_WARPS * M::PPW;
-    for (long long pt = ((long long)blockIdx.x * EC_WARPS + warp) * M::PPW + sub; pt < P; pt += stride) {
+    // contiguous point range of this CTA, interleaved over its warps / point slots
+    const long long per_cta = (P + gridDim.x - 1) / gridDim.x;
+    const long long p_begin = (long long)blockIdx.x * per_cta;
+    const long long p_end = p_begin + per_cta < P ? p_begin + per_cta : P;
+    const float kf = (float)k;
+    for (long long pt = p_begin + warp * M::PPW + sub; pt < p_end; pt += EC_WARPS * M::PPW) {
         const long long cloud0 = (pt / N) * N;
         const int32_t* irow = idx + pt * k;
-        float bi[NCH], best[NCH], ysum[NCH], f1[NCH], f2[NCH];
+        // keys: a with the sign bit flipped on channels that take the minimum (gamma < 0), so the loop is a
+        // pure arg-max; four neighbours per step are reduced as a tree (one dependent step on `best` per chunk)
+        float best[NCH], S1[NCH];
         int barg[NCH];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) FsRow<TT>::load(table + pt * ld + CP + M::chan(l, v), bi + v * VEC);
-#pragma unroll
-        for (int e = 0; e < NCH; ++e) {
-            best[e] = use_max[e] ? -INFINITY : INFINITY;
-            barg[e] = 0; ysum[e] = 0.f; f1[e] = 0.f; f2[e] = 0.f;
-        }
+        for (int e = 0; e < NCH; ++e) { best[e] = -INFINITY; barg[e] = 0; S1[e] = 0.f; }
+        const int klast = __ldg(irow + k - 1);
         for (int t0 = 0; t0 < k; t0 += 4) {
             int jn[4];
+            float w[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) jn[u] = (t0 + u < k) ? __ldg(irow + t0 + u) : -1;
+            for (int u = 0; u < 4; ++u) {
+                const bool in = t0 + u < k;
+                jn[u] = in ? __ldg(irow + t0 + u) : klast;      // tail: repeat the last neighbour (max unchanged),
+                w[u] = in ? 1.f : 0.f;                          //       weight 0 in the sum
+            }
             float a[4][NCH];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (jn[u] >= 0) {
 #pragma unroll
-                    for (int v = 0; v < NV; ++v)
-                        FsRow<TT>::load(table + (cloud0 + jn[u]) * ld + M::chan(l, v), a[u] + v * VEC);
-                }
+                for (int v = 0; v < NV; ++v)
+                    FsRow<TT>::load(table + (cloud0 + jn[u]) * ld + M::chan(l, v), a[u] + v * VEC);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (jn[u] >= 0) {
-#pragma unroll
-                    for (int e = 0; e < NCH; ++e) {
-                        const float av = a[u][e];
-                        const bool better = use_max[e] ? (av > best[e]) : (av < best[e]);
-                        if (better) { best[e] = av; barg[e] = t0 + u; }
-                        if (MODE == 0) {
-                            const float y = av + bi[e];
-                            ysum[e] += y;
-                            const float ys = y - pivot[e];
-                            f1[e] += ys;
-                            f2[e] = fmaf(ys, ys, f2[e]);
-                        }
-                    }
-                }
+            for (int e = 0; e < NCH; ++e) {
+                if (MODE == 0) S1[e] += fmaf(w[3], a[3][e], fmaf(w[2], a[2][e], fmaf(w[1], a[1][e], w[0] * a[0][e])));
+                const float k0 = __uint_as_float(__float_as_uint(a[0][e]) ^ flip[e]);
+                const float k1 = __uint_as_float(__float_as_uint(a[1][e]) ^ flip[e]);
+                const float k2 = __uint_as_float(__float_as_uint(a[2][e]) ^ flip[e]);
+                const float k3 = __uint_as_float(__float_as_uint(a[3][e]) ^ flip[e]);
+                const bool p01 = k1 > k0, p23 = k3 > k2;
+                const float m01 = fmaxf(k0, k1), m23 = fmaxf(k2, k3);
+                const bool pm = m23 > m01;
+                const float m = fmaxf(m01, m23);
+                const int am = pm ? (p23 ? 3 : 2) : (p01 ? 1 : 0);
+                const bool better = m > best[e];
+                best[e] = better ? m : best[e];
+                barg[e] = better ? t0 + am : barg[e];
             }
         }
+#pragma unroll
+        for (int e = 0; e < NCH; ++e) best[e] = __uint_as_float(__float_as_uint(best[e]) ^ flip[e]);
+        float bi[NCH];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) FsRow<TT>::load(table + pt * ld + CP + M::chan(l, v), bi + v * VEC);
         if (MODE == 0) {
+            float sy[NCH];
+#pragma unroll
+            for (int e = 0; e < NCH; ++e) sy[e] = fmaf(kf, bi[e], S1[e]);
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const int c0 = M::chan(l, v);
-                FsRow<float>::store(sel_out + pt * CP + c0, best + v * VEC);
-                if (VEC == 8) FsRow<float>::store(sel_out + pt * CP + c0 + 4, best + v * VEC + 4);
-                if (sy_out) {
-                    FsRow<float>::store(sy_out + pt * CP + c0, ysum + v * VEC);
-                    if (VEC == 8) FsRow<float>::store(sy_out + pt * CP + c0 + 4, ysum + v * VEC + 4);
+#pragma unroll
+                for (int h = 0; h < VEC; h += 4) {
+                    FsRow<float>::store(sel_out + pt * CP + c0 + h, best + v * VEC + h);
+                    if (sy_out) FsRow<float>::store(sy_out + pt * CP + c0 + h, sy + v * VEC + h);
                 }
             }
+            if (stats) {
+                float ai[NCH];
 #pragma unroll
-            for (int e = 0; e < NCH; ++e) { s1[e] += (double)f1[e]; s2[e] += (double)f2[e]; }
+                for (int v = 0; v < NV; ++v) FsRow<TT>::load(table + pt * ld + M::chan(l, v), ai + v * VEC);
+                const double deg = (double)(__ldg(rev_ptr + pt + 1) - __ldg(rev_ptr + pt));
+                const double kd = (double)k;
+#pragma unroll
+                for (int e = 0; e < NCH; ++e) {
+                    const double ap = (double)ai[e] - (double)pa[e];
+                    const double bp = (double)bi[e] - (double)pb[e];
+                    const double S1p = (double)S1[e] - kd * (double)pa[e];
+                    s1[e] += S1p + kd * bp;
+                    s2[e] += deg * ap * ap + bp * (kd * bp + 2.0 * S1p);
+                }
+            }
         } else {
             float o[NCH];
 #pragma unroll
@@ -186,12 +215,9 @@ edgeconv_gather_kernel(const TT* __restrict__ table, int ld, const int32_t* __re
     }
     if (MODE == 0 && stats) {
         fs_stats_commit<NCH>(red, s1, s2, chans, M::LPP, CP, stats);
-        if (blockIdx.x == 0) {
-            __syncthreads();
-            if (warp == 0 && sub == 0) {
+        if (blockIdx.x == 0 && warp == 0 && sub == 0) {
 #pragma unroll
-                for (int e = 0; e < NCH; ++e) stats[2 * CP + chans[e]] = (double)pivot[e];
-            }
+            for (int e = 0; e < NCH; ++e) stats[2 * CP + chans[e]] = (double)pa[e] + (double)pb[e];
         }
     }
 }
@@ -607,6 +633,13 @@ edge_reduce_bwd_kernel(const ZT* __restrict__ z, const float* __restrict__ d, co
     }
 }
 
+// contiguous point ranges: a multiple of the SM count, at least one pass of points per CTA
+int gather_grid(long long P, int points_per_pass) {
+    long long need = (P + points_per_pass - 1) / points_per_pass;
+    const long long cap = (long long)FS_NUM_SMS * 4;
+    return (int)(need < 1 ? 1 : (need > cap ? cap : need));
+}
+
 int ec_grid(long long rows, int rows_per_block) {
     long long need = (rows + rows_per_block - 1) / rows_per_block;
     long long cap = (long long)FS_NUM_SMS * 8;
@@ -634,10 +667,11 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
     }
 
 extern "C" int fs_edgeconv_gather(int device, fs_stream_t stream_, const void* table, int dtype, int ld,
-                                  const int32_t* idx, int B, int N, int k, int Cp, const float* gamma, float* sel,
-                                  uint8_t* arg, float* sy, double* stats) {
+                                  const int32_t* idx, int B, int N, int k, int Cp, const float* gamma,
+                                  const int32_t* rev_ptr, float* sel, uint8_t* arg, float* sy, double* stats) {
     EC_CHECK_COMMON(table, ld, Cp);
     if (!idx || !gamma || !sel || !arg || B < 0 || N <= 0 || k <= 0 || k > 255) return FS_ERR_BAD_ARG;
+    if (stats && !rev_ptr) return FS_ERR_BAD_ARG;
     const int esz = dtype == FS_BF16 ? 2 : 4;
     if (!aligned16(table) || (ld * esz) % 16 != 0 || !aligned16(sel)) return FS_ERR_ALIGNMENT;
     if (B == 0) return FS_OK;
@@ -647,12 +681,12 @@ extern "C" int fs_edgeconv_gather(int device, fs_stream_t stream_, const void* t
 #define GO(CP)                                                                                                  \
     if (dtype == FS_BF16) {                                                                                     \
         using M = EcMap<__nv_bfloat16, CP>;                                                                     \
-        edgeconv_gather_kernel<__nv_bfloat16, CP, 0, float><<<ec_grid(P, EC_WARPS * M::PPW), EC_THREADS, 0, stream>>>( \
-            (const __nv_bfloat16*)table, ld, idx, P, N, k, gamma, sel, arg, sy, stats, nullptr, 0);             \
+        edgeconv_gather_kernel<__nv_bfloat16, CP, 0, float><<<gather_grid(P, EC_WARPS * M::PPW), EC_THREADS, 0, stream>>>( \
+            (const __nv_bfloat16*)table, ld, idx, P, N, k, gamma, rev_ptr, sel, arg, sy, stats, nullptr, 0);             \
     } else {                                                                                                    \
         using M = EcMap<float, CP>;                                                                             \
-        edgeconv_gather_kernel<float, CP, 0, float><<<ec_grid(P, EC_WARPS * M::PPW), EC_THREADS, 0, stream>>>(  \
-            (const float*)table, ld, idx, P, N, k, gamma, sel, arg, sy, stats, nullptr, 0);                     \
+        edgeconv_gather_kernel<float, CP, 0, float><<<gather_grid(P, EC_WARPS * M::PPW), EC_THREADS, 0, stream>>>(  \
+            (const float*)table, ld, idx, P, N, k, gamma, rev_ptr, sel, arg, sy, stats, nullptr, 0);                     \
     }
     EC_DISPATCH_CP(Cp, GO)
 #undef GO
@@ -674,8 +708,8 @@ extern "C" int fs_edgeconv_fused_eval(int device, fs_stream_t stream_, const voi
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long P = (long long)B * N;
 #define GO2(CP, TT, OT)                                                                                         \
-    edgeconv_gather_kernel<TT, CP, 1, OT><<<ec_grid(P, EC_WARPS * EcMap<TT, CP>::PPW), EC_THREADS, 0, stream>>>( \
-        (const TT*)table, ld, idx, P, N, k, coef, nullptr, arg, nullptr, nullptr, (OT*)out, ld_out)
+    edgeconv_gather_kernel<TT, CP, 1, OT><<<gather_grid(P, EC_WARPS * EcMap<TT, CP>::PPW), EC_THREADS, 0, stream>>>( \
+        (const TT*)table, ld, idx, P, N, k, coef, nullptr, nullptr, arg, nullptr, nullptr, (OT*)out, ld_out)
 #define GO(CP)                                                                      \
     if (dtype == FS_BF16 && out_dtype == FS_BF16) GO2(CP, __nv_bfloat16, __nv_bfloat16); \
     else if (dtype == FS_BF16) GO2(CP, __nv_bfloat16, float);                       \

@@ -138,8 +138,9 @@ class _EdgeConvFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[:3])
         sy = torch.empty(P, Cp, dtype=torch.float32, device=dev) if (training and need_grad) else None
         stats = _stats_buffer(Cp, dev) if training else None
-        _lib.call("fs_edgeconv_gather", table, table, dt, table.stride(0), idx, B, N, k, Cp, gamma32, sel, arg, sy,
-                  stats)
+        rev_ptr = graph.reverse()[0] if training else None      # in-degrees for the batch statistics
+        _lib.call("fs_edgeconv_gather", table, table, dt, table.stride(0), idx, B, N, k, Cp, gamma32, rev_ptr, sel, arg,
+                  sy, stats)
         coef = _bn_coef(table, stats, P * k, gamma32, beta32, running_mean, running_var, nbt, training, Cp, eps,
                         momentum)
         out = torch.empty(P, Cp, dtype=table.dtype, device=dev)

@@ -124,6 +124,7 @@ int fs_furthestsampling(int device, fs_stream_t stream, int b, const float* xyz,
  */
 int fs_edgeconv_gather(int device, fs_stream_t stream, const void* table, int dtype, int ld,
                        const int32_t* idx, int B, int N, int k, int Cp, const float* gamma,
+                       const int32_t* rev_ptr /* in-degrees from fs_reverse_graph; required with stats */,
                        float* sel, uint8_t* arg, float* sy, double* stats);
 
 /*
