@@ -175,6 +175,33 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// 30-bit Morton (Z-order) code of the first three channels, 10 bits per axis over the fixed box [-2, 2)^3
+// (grid coordinates live in [-1, 1] before augmentation, augmentations.py:52-75).
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void morton_kernel(const float* __restrict__ coords, long long bs, long long cs, long long ps, int N,
+                              long long total, int32_t* __restrict__ codes) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / N;
+        const long long n = e - b * N;
+        const float* p = coords + b * bs + n * ps;
+        uint32_t q[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = (__ldg(p + c * cs) + 2.0f) * 256.0f;          // [-2,2) -> [0,1024)
+            v = v != v ? 0.f : fminf(fmaxf(v, 0.f), 1023.f);        // NaN -> 0, clamp
+            q[c] = (uint32_t)v;
+        }
+        codes[e] = (int32_t)(spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2));
+    }
+}
+
 int flat_grid(long long total) {
     long long g = (total + 255) / 256;
     const long long cap = (long long)FS_NUM_SMS * 16;
@@ -261,6 +288,19 @@ extern "C" int fs_aggregation_bwd(int device, fs_stream_t stream_, int n, int ns
         return FS_ERR_BAD_ARG;
     FLAT_LAUNCH(aggregation_bwd_kernel, (long long)n * c, nsample, c, w_c, in, pos, weight, idx, grad_out, grad_in,
                 grad_pos, grad_weight);
+}
+
+extern "C" int fs_morton_codes(int device, fs_stream_t stream_, const float* coords, long long batch_stride,
+                               long long chan_stride, long long point_stride, int B, int N, int32_t* codes) {
+    if (B < 0 || N < 0) return FS_ERR_BAD_ARG;
+    if (B == 0 || N == 0) return FS_OK;
+    if (!coords || !codes) return FS_ERR_BAD_ARG;
+    FS_ENTER(device);
+    const long long total = (long long)B * N;
+    morton_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream_>>>(coords, batch_stride, chan_stride, point_stride, N,
+                                                                     total, codes);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
 }
 
 extern "C" int fs_adam_step(int device, fs_stream_t stream_, float* param, const float* grad, float* exp_avg,

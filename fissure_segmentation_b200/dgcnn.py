@@ -258,7 +258,12 @@ class DGCNNBase(PointSegmentationModelBase):
         self.k = k
         self.dynamic = dynamic
         self._graph = None
+        self._perm = None
         self.precision = "auto"   # 'auto' | 'fp32' | 'bf16'
+        # Sort every cloud along the Morton curve of its coordinates before the EdgeConvs: consecutive rows are
+        # then spatial neighbours and the k-row gathers of a CTA's point range overlap (L1/L2 hits). Every
+        # operator is permutation-equivariant; per-point outputs are un-permuted before they are returned.
+        self.spatial_sort = True
 
         if image_feat_module:
             if in_features < 4:
@@ -275,10 +280,32 @@ class DGCNNBase(PointSegmentationModelBase):
 
     @property
     def knn_graph(self):
-        """Static graph of the last forward as the reference exposes it: int64 (B, N, k) or None."""
-        return None if self._graph is None else self._graph.idx.long()
+        """Static graph of the last forward as the reference exposes it: int64 (B, N, k) or None,
+        in the caller's point numbering."""
+        if self._graph is None:
+            return None
+        idx = self._graph.idx.long()
+        if self._perm is None:
+            return idx
+        B, N, k = idx.shape
+        orig = torch.gather(self._perm, 1, idx.reshape(B, N * k)).view(B, N, k)      # neighbour ids -> original
+        out = torch.empty_like(orig)
+        out.scatter_(1, self._perm.unsqueeze(-1).expand(B, N, k), orig)              # rows -> original
+        return out
+
+    def _unsort_points(self, y):
+        """(B, C, N) in sorted order -> the caller's order."""
+        if self._perm is None:
+            return y
+        out = torch.empty_like(y)
+        return out.scatter(2, self._perm.unsqueeze(1).expand_as(y), y)
 
     def forward(self, x):
+        self._perm = None
+        if self.spatial_sort and x.is_cuda and x.shape[1] >= 3:
+            with torch.no_grad():
+                self._perm = ops.spatial_order(x.detach())
+            x = torch.gather(x, 2, self._perm.unsqueeze(1).expand_as(x))
         if not self.dynamic:
             with torch.no_grad():
                 self._graph = KnnGraph(ops.knn_coords(x.detach(), self.k, self_loop=False))
@@ -337,7 +364,7 @@ class DGCNNSeg(DGCNNBase):
             h = self.segmentation[1].forward_pm(h)
             h = self.segmentation[2].forward_pm(h)
             logits = self.segmentation[3].forward_pm(h)                          # (B*N, classes)
-            return logits.view(B, N, -1).permute(0, 2, 1).float()
+            return self._unsort_points(logits.view(B, N, -1).permute(0, 2, 1).float())
 
 
 class DGCNNReg(DGCNNBase):

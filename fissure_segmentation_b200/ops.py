@@ -90,6 +90,15 @@ def knn_features(feat, B, N, k, self_loop=False, diag_zero=True, return_dist=Fal
     return (idx, dist) if return_dist else idx
 
 
+def spatial_order(x):
+    """Permutation (B, N) int64 that sorts every cloud of x (B, C>=3, N) along the Morton curve of its xyz."""
+    B, _, N = x.shape
+    codes = torch.empty(B, N, dtype=torch.int32, device=x.device)
+    xf = x if x.dtype == torch.float32 else x.float()
+    _lib.call("fs_morton_codes", xf, xf, xf.stride(0), xf.stride(1), xf.stride(2), B, N, codes)
+    return torch.sort(codes, dim=1, stable=True)[1]
+
+
 def to_point_major(x):
     """(B, C, N) -> contiguous (B*N, C)."""
     B, C, N = x.shape

@@ -109,6 +109,15 @@ int fs_knnquery(int device, fs_stream_t stream, int m, int nsample, const float*
 int fs_furthestsampling(int device, fs_stream_t stream, int b, const float* xyz,
                         const int32_t* offset, const int32_t* new_offset, float* tmp, int32_t* idx);
 
+/*
+ * 30-bit Morton (Z-order) code of the xyz channels of each point (box [-2,2)^3, 10 bits per axis). The
+ * modules sort every cloud by this code before the EdgeConvs so that the neighbour rows of consecutive
+ * points overlap (L1/L2 locality of the gathers); all operators are permutation-equivariant, the logits are
+ * un-permuted at the end. Same addressing as fs_knn3d.
+ */
+int fs_morton_codes(int device, fs_stream_t stream, const float* coords, long long batch_stride,
+                    long long chan_stride, long long point_stride, int B, int N, int32_t* codes);
+
 /* ---------------------------------------------------------------- fused EdgeConv ----------- */
 
 /*

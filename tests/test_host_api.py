@@ -26,7 +26,7 @@ def test_entry_points_reject_bad_arguments_without_launching(lib):
     assert lib.fs_knn3d(0, None, None, 0, 0, 0, 1, 16, 4, 1, 1, None, None) == -1
     assert lib.fs_knnquery(0, None, 4, 4, None, None, None, None, 1, None, None) == -1
     assert lib.fs_nn_points(0, None, None, None, 1, 4, 4, None, None) == -1
-    assert lib.fs_edgeconv_gather(0, None, None, 0, 128, None, 1, 4, 2, 64, None, None, None, None, None) == -1
+    assert lib.fs_edgeconv_gather(0, None, None, 0, 128, None, 1, 4, 2, 64, None, None, None, None, None, None) == -1
 
 
 def test_no_cpu_fallback():
