@@ -37,7 +37,10 @@ constexpr int TC_ABOX_BYTES = TC_M * 128;
 constexpr int TC_ATILE_BYTES = TC_BOXES * TC_ABOX_BYTES;     // 64 KB
 constexpr int TC_BBOX_BYTES = TC_NB * 128;
 constexpr int TC_BTILE_BYTES = TC_BOXES * TC_BBOX_BYTES;     // 32 KB
-constexpr int TC_STAGES = 2;
+constexpr int TC_STAGES = 6;         // smem stages of the candidate (B) tiles (32 KB each)
+constexpr int TC_ACC = 2;            // TMEM accumulator buffers (each holds TC_QT tiles of TC_NB columns)
+constexpr int TC_KSTEPS = 13;        // K = 16 steps: 12 data (hi*hi, lo*hi, hi*lo) + 1 extras
+constexpr int TC_A_COLS = TC_KSTEPS * 8;   // TMEM columns of one query tile's A operand (2 bf16 per 32-bit column)
 constexpr int TC_EPI_WARPS = 4 * TC_QT;   // one epilogue warpgroup per query tile (TMEM lane = query row)
 constexpr int TC_WARP_TMA = TC_EPI_WARPS;
 constexpr int TC_WARP_MMA = TC_EPI_WARPS + 1;
@@ -46,9 +49,11 @@ constexpr int TC_STAGE_BYTES = 32 * 32 * 4;  // per-warp staging of one 32 x 32 
 constexpr int TC_CAP = 64;         // survivor slots per query
 constexpr int TC_NCLS = 32;        // interleaved column classes of sweep 1
 constexpr int TC_MAX_KK = 24;      // kk-th smallest of 32 class minima stays near rank 1.6 kk up to here
-constexpr int TC_TMEM_COLS = TC_STAGES * TC_QT * TC_NB;      // 256
-constexpr int TC_SMEM_BYTES = TC_QT * TC_ATILE_BYTES + TC_STAGES * TC_BTILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-                              TC_EPI_WARPS * TC_STAGE_BYTES;
+constexpr int TC_TMEM_ACC0 = 256;     // accumulators at columns [256, 512), A operands at [0, 2*104)
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_BTILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * TC_STAGE_BYTES;
+static_assert(TC_QT * TC_A_COLS <= TC_TMEM_ACC0 && TC_TMEM_ACC0 + TC_ACC * TC_QT * TC_NB <= TC_TMEM_COLS, "TMEM budget");
+static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget");
 
 constexpr float TC_ERR_CENTRED = 6.2e-5f;   // 2^-14: bound of the bf16 hi/lo product error, per (|xi|^2+|xj|^2)
 constexpr float TC_ERR_RAW = 1.0e-6f;       // rounding of the exact FP32 expansion form, per raw squared norm
@@ -129,6 +134,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ----------------------------------------------------------------------------------------------- prep
 __global__ void tc_colsum_kernel(const float* __restrict__ x, int ldx, int N, float* __restrict__ sums) {
     // grid (chunks, B), block 256 = 4 row-groups x 64 channels
@@ -150,51 +171,82 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& h, __nv_bfloat16&
     l2 = __float2bfloat16_rn(r1 - __bfloat162float(l));
 }
 
-// One warp per point: lane handles channels 2*lane, 2*lane+1 of the operand rows; the raw squared norm is
-// summed exactly like row_sqnorm_kernel (knn.cu) so the exact re-evaluation matches the exact kernel bit for bit.
+// One warp per 4 consecutive points (four independent row loads in flight per lane): lane handles channels
+// 2*lane, 2*lane+1 of the operand rows; the raw squared norm is summed exactly like row_sqnorm_kernel (knn.cu)
+// so the exact re-evaluation matches the exact kernel bit for bit.
+constexpr int TC_SPLIT_ROWS = 4;
 __global__ void __launch_bounds__(256)
 tc_split_kernel(const float* __restrict__ x, int ldx, long long P, int N, const float* __restrict__ sums,
                 __nv_bfloat16* __restrict__ A, __nv_bfloat16* __restrict__ Bm, float* __restrict__ cnorm,
                 float* __restrict__ sqnorm, int* __restrict__ norm_max_bits /* [B][2]: centred, raw */) {
-    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= P) return;
+    // per-cloud maxima of the norms: one atomic per block and cloud instead of one per row (the per-row version
+    // serialised 2048 atomics on each address and dominated the kernel)
+    __shared__ int s_max[2];
+    const long long blk_row0 = (long long)blockIdx.x * 8 * TC_SPLIT_ROWS;
+    const long long blk_row1 = blk_row0 + 8 * TC_SPLIT_ROWS - 1 < P - 1 ? blk_row0 + 8 * TC_SPLIT_ROWS - 1 : P - 1;
+    const bool one_cloud = blk_row0 / N == blk_row1 / N;
+    if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
+    __syncthreads();
+    const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * TC_SPLIT_ROWS;
     const int lane = threadIdx.x & 31;
-    const int b = (int)(row / N);
     const float inv_n = 1.0f / (float)N;
-    const float2 xv = *reinterpret_cast<const float2*>(x + row * ldx + 2 * lane);
-    const float v0 = xv.x - __ldg(sums + b * TC_C + 2 * lane) * inv_n;
-    const float v1 = xv.y - __ldg(sums + b * TC_C + 2 * lane + 1) * inv_n;
-    __nv_bfloat16 h0, l0, t0, h1, l1, t1;
-    split3(v0, h0, l0, t0);
-    split3(v1, h1, l1, t1);
-    // the norm that rides in the GEMM is the norm of the values the GEMM actually multiplies (hi + lo)
-    const float e0 = __bfloat162float(h0) + __bfloat162float(l0), e1 = __bfloat162float(h1) + __bfloat162float(l1);
-    const float nrm = fs_warp_sum(e0 * e0 + e1 * e1);
-    const float ra = __ldg(x + row * ldx + lane), rb = __ldg(x + row * ldx + lane + 32);
-    const float raw = fs_warp_sum(__fadd_rn(__fadd_rn(0.f, __fmul_rn(ra, ra)), __fmul_rn(rb, rb)));
-    __nv_bfloat162* Ar = reinterpret_cast<__nv_bfloat162*>(A + row * TC_KROW);
-    __nv_bfloat162* Br = reinterpret_cast<__nv_bfloat162*>(Bm + row * TC_KROW);
-    const __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
-    const __nv_bfloat162 hh2 = __hmul2(hh, __float2bfloat162_rn(-2.0f)), ll2 = __hmul2(ll, __float2bfloat162_rn(-2.0f));
-    Ar[lane] = hh;        Br[lane] = hh2;        // hi * hi
-    Ar[32 + lane] = ll;   Br[32 + lane] = hh2;   // lo * hi
-    Ar[64 + lane] = hh;   Br[64 + lane] = ll2;   // hi * lo
-    // extras: A = [1 1 1 n_h n_l n_l2 0...], B = [n_h n_l n_l2 1 1 1 0...]
-    __nv_bfloat16 nh, nl, nl2;
-    split3(nrm, nh, nl, nl2);
-    const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
-    __nv_bfloat16 ea0 = zero, ea1 = zero, eb0 = zero, eb1 = zero;
-    if (lane == 0) { ea0 = one; ea1 = one; eb0 = nh; eb1 = nl; }
-    if (lane == 1) { ea0 = one; ea1 = nh; eb0 = nl2; eb1 = one; }
-    if (lane == 2) { ea0 = nl; ea1 = nl2; eb0 = one; eb1 = one; }
-    Ar[96 + lane] = __halves2bfloat162(ea0, ea1);
-    Br[96 + lane] = __halves2bfloat162(eb0, eb1);
-    if (lane == 0) {
-        cnorm[row] = nrm;
-        sqnorm[row] = raw;
-        atomicMax(norm_max_bits + 2 * b, __float_as_int(nrm));
-        atomicMax(norm_max_bits + 2 * b + 1, __float_as_int(raw));
+    if (row0 < P) {
+    float2 xv[TC_SPLIT_ROWS];
+    float ra[TC_SPLIT_ROWS], rb[TC_SPLIT_ROWS];
+#pragma unroll
+    for (int r = 0; r < TC_SPLIT_ROWS; ++r) {
+        const long long row = row0 + r < P ? row0 + r : P - 1;
+        xv[r] = __ldg(reinterpret_cast<const float2*>(x + row * ldx + 2 * lane));
+        ra[r] = __ldg(x + row * ldx + lane);
+        rb[r] = __ldg(x + row * ldx + lane + 32);
     }
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
+    const __nv_bfloat162 m2 = __float2bfloat162_rn(-2.0f);
+#pragma unroll
+    for (int r = 0; r < TC_SPLIT_ROWS; ++r) {
+        const long long row = row0 + r;
+        if (row >= P) break;
+        const int b = (int)(row / N);
+        const float v0 = xv[r].x - __ldg(sums + b * TC_C + 2 * lane) * inv_n;
+        const float v1 = xv[r].y - __ldg(sums + b * TC_C + 2 * lane + 1) * inv_n;
+        __nv_bfloat16 h0, l0, t0, h1, l1, t1;
+        split3(v0, h0, l0, t0);
+        split3(v1, h1, l1, t1);
+        // the norm that rides in the GEMM is the norm of the values the GEMM actually multiplies (hi + lo)
+        const float e0 = __bfloat162float(h0) + __bfloat162float(l0), e1 = __bfloat162float(h1) + __bfloat162float(l1);
+        const float nrm = fs_warp_sum(e0 * e0 + e1 * e1);
+        const float raw = fs_warp_sum(__fadd_rn(__fadd_rn(0.f, __fmul_rn(ra[r], ra[r])), __fmul_rn(rb[r], rb[r])));
+        __nv_bfloat162* Ar = reinterpret_cast<__nv_bfloat162*>(A + row * TC_KROW);
+        __nv_bfloat162* Br = reinterpret_cast<__nv_bfloat162*>(Bm + row * TC_KROW);
+        const __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
+        const __nv_bfloat162 hh2 = __hmul2(hh, m2), ll2 = __hmul2(ll, m2);
+        Ar[lane] = hh;        Br[lane] = hh2;        // hi * hi
+        Ar[32 + lane] = ll;   Br[32 + lane] = hh2;   // lo * hi
+        Ar[64 + lane] = hh;   Br[64 + lane] = ll2;   // hi * lo
+        // extras: A = [1 1 1 n_h n_l n_l2 0...], B = [n_h n_l n_l2 1 1 1 0...]
+        __nv_bfloat16 nh, nl, nl2;
+        split3(nrm, nh, nl, nl2);
+        __nv_bfloat16 ea0 = zero, ea1 = zero, eb0 = zero, eb1 = zero;
+        if (lane == 0) { ea0 = one; ea1 = one; eb0 = nh; eb1 = nl; }
+        if (lane == 1) { ea0 = one; ea1 = nh; eb0 = nl2; eb1 = one; }
+        if (lane == 2) { ea0 = nl; ea1 = nl2; eb0 = one; eb1 = one; }
+        Ar[96 + lane] = __halves2bfloat162(ea0, ea1);
+        Br[96 + lane] = __halves2bfloat162(eb0, eb1);
+        if (lane == 0) {
+            cnorm[row] = nrm;
+            sqnorm[row] = raw;
+            if (one_cloud) {
+                atomicMax(&s_max[0], __float_as_int(nrm));
+                atomicMax(&s_max[1], __float_as_int(raw));
+            } else {
+                atomicMax(norm_max_bits + 2 * b, __float_as_int(nrm));
+                atomicMax(norm_max_bits + 2 * b + 1, __float_as_int(raw));
+            }
+        }
+    }
+    }
+    __syncthreads();
+    if (one_cloud && threadIdx.x < 2) atomicMax(norm_max_bits + 2 * (int)(blk_row0 / N) + threadIdx.x, s_max[threadIdx.x]);
 }
 
 __device__ __forceinline__ float tc_row_err(float cn, float cmax, float rn, float rmax) {
@@ -226,18 +278,41 @@ __device__ __forceinline__ void bitonic_sort32(float (&g)[32]) {
 }
 
 // ----------------------------------------------------------------------------------------------- select
+// tcgen05.mma with the A operand (queries) in TMEM: D[tmem] (+)= A[tmem] * B[smem].
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& lo, const uint4& hi) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
+
+// Shared-memory bandwidth is the scarce resource of this kernel (an SS-mode MMA re-reads its 128-row A slab for
+// every 64 candidates), so the query operands live in TMEM (TS mode): each epilogue thread copies its own query
+// row (TMEM lane = row) from global memory with tcgen05.st once, and shared memory only carries the streamed
+// candidate tiles (6 TMA stages) plus the sweep-2 staging blocks.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-knn_tc_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int N, int kk,
-                     int diag_zero, const float* __restrict__ cnorm, const float* __restrict__ sqnorm,
+knn_tc_select_kernel(const __nv_bfloat16* __restrict__ a_rows, long long P, const __grid_constant__ CUtensorMap map_b,
+                     int N, int kk, int diag_zero, const float* __restrict__ cnorm, const float* __restrict__ sqnorm,
                      const int* __restrict__ norm_max_bits, int32_t* __restrict__ cand_j, float* __restrict__ cand_d,
                      int32_t* __restrict__ cand_n) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + TC_QT * TC_ATILE_BYTES;
+    uint8_t* smem_b = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + TC_STAGES * TC_BTILE_BYTES);
-    // bars: 0 a_full | 1,2 b_full | 3,4 b_empty | 5,6 acc_full | 7,8 acc_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    // bars: b_full[STAGES] | b_empty[STAGES] | acc_full[ACC] | acc_empty[ACC] | a_full
+    uint64_t* b_full = bars;
+    uint64_t* b_empty = bars + TC_STAGES;
+    uint64_t* acc_full = bars + 2 * TC_STAGES;
+    uint64_t* acc_empty = acc_full + TC_ACC;
+    uint64_t* a_full = acc_empty + TC_ACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
     float* stage_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5;
@@ -248,13 +323,9 @@ knn_tc_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int q_row0 = blockIdx.x * (TC_QT * TC_M);
 
     if (threadIdx.x == 0) {
-        mbar_init(smem_u32(bars + 0), 1);
-        for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(smem_u32(bars + 1 + s), 1);
-            mbar_init(smem_u32(bars + 3 + s), 1);
-            mbar_init(smem_u32(bars + 5 + s), 1);
-            mbar_init(smem_u32(bars + 7 + s), TC_EPI_WARPS);
-        }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(b_full + s), 1); mbar_init(smem_u32(b_empty + s), 1); }
+        for (int a = 0; a < TC_ACC; ++a) { mbar_init(smem_u32(acc_full + a), 1); mbar_init(smem_u32(acc_empty + a), TC_EPI_WARPS); }
+        mbar_init(smem_u32(a_full), TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_WARP_MMA) {
@@ -269,49 +340,42 @@ knn_tc_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == TC_WARP_TMA) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-            mbar_expect_tx(smem_u32(bars + 0), TC_QT * TC_ATILE_BYTES);
-            for (int u = 0; u < TC_QT; ++u)
-                for (int bx = 0; bx < TC_BOXES; ++bx)
-                    tma_load_2d(smem_u32(smem_a + u * TC_ATILE_BYTES + bx * TC_ABOX_BYTES), &map_a, smem_u32(bars + 0),
-                                bx * 64, (int)(cloud0 + q_row0 + u * TC_M));
             for (int it = 0; it < 2 * T; ++it) {
                 const int s = it % TC_STAGES;
                 const uint32_t ph = (it / TC_STAGES) & 1;
-                mbar_wait(smem_u32(bars + 3 + s), ph ^ 1);
-                mbar_expect_tx(smem_u32(bars + 1 + s), TC_BTILE_BYTES);
+                mbar_wait(smem_u32(b_empty + s), ph ^ 1);
+                mbar_expect_tx(smem_u32(b_full + s), TC_BTILE_BYTES);
                 const int row = (int)(cloud0 + (it % T) * TC_NB);
                 for (int bx = 0; bx < TC_BOXES; ++bx)
-                    tma_load_2d(smem_u32(smem_b + s * TC_BTILE_BYTES + bx * TC_BBOX_BYTES), &map_b, smem_u32(bars + 1 + s),
+                    tma_load_2d(smem_u32(smem_b + s * TC_BTILE_BYTES + bx * TC_BBOX_BYTES), &map_b, smem_u32(b_full + s),
                                 bx * 64, row);
             }
         }
     } else if (warp == TC_WARP_MMA) {
-        // ===================== MMA issuer =====================
-        mbar_wait(smem_u32(bars + 0), 0);
+        // ===================== MMA issuer: one thread, straight-line issue (descriptors = base + constant) ========
+        mbar_wait(smem_u32(a_full), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b));
         for (int it = 0; it < 2 * T; ++it) {
             const int s = it % TC_STAGES;
-            const uint32_t ph = (it / TC_STAGES) & 1;
-            mbar_wait(smem_u32(bars + 1 + s), ph);          // operands landed
-            mbar_wait(smem_u32(bars + 7 + s), ph ^ 1);      // accumulators of this stage drained by the epilogue
+            const int a = it % TC_ACC;
+            mbar_wait(smem_u32(b_full + s), (it / TC_STAGES) & 1);            // operands landed
+            mbar_wait(smem_u32(acc_empty + a), ((it / TC_ACC) & 1) ^ 1);      // accumulator buffer drained by the epilogue
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                for (int u = 0; u < TC_QT; ++u) {
-                    const uint32_t acc = tmem_base + (s * TC_QT + u) * TC_NB;
-                    uint32_t accumulate = 0;
-                    for (int bx = 0; bx < TC_BOXES; ++bx) {
-                        const int nk = bx < 3 ? 4 : 1;      // extras box: only its first 16 K columns are non-zero
-                        for (int kq = 0; kq < nk; ++kq) {
-                            const uint64_t da = umma_desc_sw128(smem_u32(smem_a + u * TC_ATILE_BYTES + bx * TC_ABOX_BYTES) + kq * 32);
-                            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * TC_BTILE_BYTES + bx * TC_BBOX_BYTES) + kq * 32);
-                            umma_bf16(acc, da, db, accumulate);
-                            accumulate = 1;
-                        }
-                    }
+                const uint64_t db_s = db0 + (uint64_t)((s * TC_BTILE_BYTES) >> 4);
+                const uint32_t acc_a = tmem_base + TC_TMEM_ACC0 + a * TC_QT * TC_NB;
+#pragma unroll
+                for (int st = 0; st < TC_KSTEPS; ++st) {
+                    const int bx = st < 12 ? st / 4 : 3, kq = st < 12 ? st % 4 : 0;   // extras box: first 16 K columns only
+                    const uint64_t db = db_s + (uint64_t)((bx * TC_BBOX_BYTES + kq * 32) >> 4);
+#pragma unroll
+                    for (int u = 0; u < TC_QT; ++u)        // the two query tiles alternate: independent back-to-back MMAs
+                        umma_bf16_ts(acc_a + u * TC_NB, tmem_base + u * TC_A_COLS + st * 8, db, st ? 1u : 0u);
                 }
-                umma_commit(smem_u32(bars + 3 + s));        // smem stage free once these MMAs retire
-                umma_commit(smem_u32(bars + 5 + s));        // accumulators ready
+                umma_commit(smem_u32(b_empty + s));         // smem stage free once these MMAs retire
+                umma_commit(smem_u32(acc_full + a));        // accumulators ready
             }
             __syncwarp();
         }
@@ -321,6 +385,22 @@ knn_tc_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int w4 = warp & 3;                       // TMEM lane quarter this warp may access
         const int qrow = q_row0 + u * TC_M + w4 * 32 + lane;
         const bool row_ok = qrow < N;
+        const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
+        {
+            // A operand: this thread's query row -> TMEM (columns u*104 .. +104); rows past the table are zero
+            const long long grow = cloud0 + qrow;
+            const uint4* src = reinterpret_cast<const uint4*>(a_rows + (grow < P ? grow : 0) * TC_KROW);
+#pragma unroll
+            for (int st = 0; st < TC_KSTEPS; ++st) {
+                uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+                if (grow < P) { lo = __ldg(src + 2 * st); hi = __ldg(src + 2 * st + 1); }
+                tmem_st8(tmem_base + lane_base + (uint32_t)(u * TC_A_COLS + st * 8), lo, hi);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(a_full));
+        }
         float* stage = stage_all + warp * (TC_STAGE_BYTES / 4) + lane * 32;   // this thread's 32 staged scores
         float gm[TC_NCLS];
 #pragma unroll
@@ -329,8 +409,8 @@ knn_tc_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         int cnt = 0;
         const long long out_base = (cloud0 + (row_ok ? qrow : 0)) * TC_CAP;
         for (int it = 0; it < 2 * T; ++it) {
-            const int s = it % TC_STAGES;
-            const uint32_t ph = (it / TC_STAGES) & 1;
+            const int a = it % TC_ACC;
+            const uint32_t ph = (it / TC_ACC) & 1;
             const int j0 = (it % T) * TC_NB;
             if (it == T) {
                 // between the sweeps: tau = kk-th smallest class minimum (+ 2 err); bitonic network in registers
@@ -342,50 +422,59 @@ knn_tc_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int q = row_ok ? qrow : N - 1;
                 tau = t + 2.f * tc_row_err(__ldg(cnorm + cloud0 + q), cmax, __ldg(sqnorm + cloud0 + q), rmax);
             }
-            mbar_wait(smem_u32(bars + 5 + s), ph);
+            mbar_wait(smem_u32(acc_full + a), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
+            // Both 32-column blocks of this thread's row are pulled into registers and the accumulator buffer is
+            // handed back to the MMA warp BEFORE the scores are processed.
+            float v[TC_NB / 32][32];
+#pragma unroll
+            for (int cb = 0; cb < TC_NB / 32; ++cb)
+                tmem_ld32_nowait(tmem_base + lane_base + (uint32_t)(TC_TMEM_ACC0 + (a * TC_QT + u) * TC_NB + cb * 32), v[cb]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(acc_empty + a));
+#pragma unroll
             for (int cb = 0; cb < TC_NB / 32; ++cb) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)((s * TC_QT + u) * TC_NB + cb * 32), v);
                 const int jb = j0 + cb * 32;
                 if (jb + 32 > N) {         // last tile: columns beyond the cloud are padding / the next cloud
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = (jb + e < N) ? v[e] : INFINITY;
+                    for (int e = 0; e < 32; ++e) v[cb][e] = (jb + e < N) ? v[cb][e] : INFINITY;
                 }
                 if (diag_zero && __any_sync(FS_FULL_MASK, qrow >= jb && qrow < jb + 32)) {
                     // the reference forces d(i,i) = 0 (general_utils.py:52): the query itself always survives
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = (jb + e == qrow) ? -FLT_MAX : v[e];
+                    for (int e = 0; e < 32; ++e) v[cb][e] = (jb + e == qrow) ? -FLT_MAX : v[cb][e];
                 }
                 if (it < T) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) gm[e] = fminf(gm[e], v[e]);
+                    for (int e = 0; e < 32; ++e) gm[e] = fminf(gm[e], v[cb][e]);
                 } else {
                     // sweep 2: branch-free hit mask, scores staged in shared memory (16-byte chunks XOR-swizzled by
                     // lane so the 128-bit stores are conflict-free), then each lane walks its own few hits
                     unsigned hits = 0;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) hits |= (v[e] <= tau) ? (1u << e) : 0u;
+                    for (int e = 0; e < 32; ++e) hits |= (v[cb][e] <= tau) ? (1u << e) : 0u;
                     if (!row_ok) hits = 0;
+                    if (__any_sync(FS_FULL_MASK, hits != 0)) {
+                        __syncwarp();
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        *reinterpret_cast<float4*>(stage + ((c ^ (lane & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                    while (hits) {
-                        const int e = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        const float dv = stage[(((e >> 2) ^ (lane & 7)) << 2) + (e & 3)];
-                        if (cnt < TC_CAP) {
-                            cand_j[out_base + cnt] = jb + e;
-                            cand_d[out_base + cnt] = dv;
+                        for (int c = 0; c < 8; ++c)
+                            *reinterpret_cast<float4*>(stage + ((c ^ (lane & 7)) << 2)) =
+                                make_float4(v[cb][4 * c], v[cb][4 * c + 1], v[cb][4 * c + 2], v[cb][4 * c + 3]);
+                        while (hits) {
+                            const int e = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            const float dv = stage[(((e >> 2) ^ (lane & 7)) << 2) + (e & 3)];
+                            if (cnt < TC_CAP) {
+                                cand_j[out_base + cnt] = jb + e;
+                                cand_d[out_base + cnt] = dv;
+                            }
+                            ++cnt;
                         }
-                        ++cnt;
                     }
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(bars + 7 + s));
         }
         if (row_ok) cand_n[cloud0 + qrow] = cnt;
     }
@@ -400,6 +489,112 @@ knn_tc_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // ----------------------------------------------------------------------------------------------- finalize
 // One warp per query: sort the survivors by approximate distance, decide everything further than 2 err
 // from the kk-th by the approximation, re-evaluate the rest exactly (reference FP32 arithmetic).
+// H = entries per lane: 1 when the row has at most 32 survivors (one 32-wide bitonic sort), else 2.
+template <int H>
+__device__ __forceinline__ void tc_finalize_row(const float* __restrict__ x, int ldx, long long cloud0, int q, long long row,
+                                                int k, int kk, int skip, int diag_zero, int n,
+                                                const int32_t* __restrict__ cand_j, const float* __restrict__ cand_d,
+                                                const float* __restrict__ sqnorm, float err, float qq,
+                                                float* qd, int* qi, float* xq, int32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    float sd[H];
+    int sj[H];
+    if (H == 1) {
+        const bool valid = lane < n;
+        sd[0] = valid ? __ldg(cand_d + row * TC_CAP + lane) : INFINITY;
+        sj[0] = valid ? __ldg(cand_j + row * TC_CAP + lane) : FS_IDX_PAD;
+        fs_warp_bitonic_sort(sd[0], sj[0], lane);
+    } else {
+        FsWarpSelect<2> sel;
+        sel.init(qd, qi, 64);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int slot = h * 32 + lane;
+            const bool valid = slot < n;
+            sel.offer(valid ? __ldg(cand_d + row * TC_CAP + slot) : INFINITY, valid ? __ldg(cand_j + row * TC_CAP + slot) : FS_IDX_PAD, valid);
+        }
+        sel.finish();
+#pragma unroll
+        for (int h = 0; h < H; ++h) { sd[h] = sel.d[h]; sj[h] = sel.i[h]; }
+    }
+    const int r_thr = kk - 1;
+    float thr = __shfl_sync(FS_FULL_MASK, sd[0], r_thr & 31);
+    if (H == 2) {
+        const float t1 = __shfl_sync(FS_FULL_MASK, sd[H - 1], r_thr & 31);
+        thr = (r_thr >> 5) ? t1 : thr;
+    }
+    const float lo = thr - 2.f * err, hi = thr + 2.f * err;
+    bool in_[H], amb[H];
+    int n_in = 0, n_amb = 0;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const bool valid = sj[h] != FS_IDX_PAD;
+        in_[h] = valid && sd[h] < lo;
+        amb[h] = valid && !in_[h] && sd[h] <= hi;
+        n_in += __popc(__ballot_sync(FS_FULL_MASK, in_[h]));
+        n_amb += __popc(__ballot_sync(FS_FULL_MASK, amb[h]));
+    }
+    const int slots = kk - n_in;
+    if (n_amb == slots) {
+        // the approximation alone decides the set: ranks [0, kk) in approximate order
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const int r = h * 32 + lane;
+            if (r >= skip && r < kk) out[r - skip] = sj[h];
+        }
+        return;
+    }
+    // ambiguous boundary: exact distances (same arithmetic as knn_feat_kernel) for the ambiguous entries
+    xq[lane] = __ldg(x + row * ldx + lane);
+    xq[lane + 32] = __ldg(x + row * ldx + lane + 32);
+    __syncwarp();
+    float ex[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        ex[h] = INFINITY;
+        if (amb[h]) {
+            const int j = sj[h];
+            const float* xr = x + (cloud0 + j) * ldx;
+            float acc = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < TC_C / 4; ++c4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + c4);
+                acc = fmaf(xq[4 * c4], v.x, acc);
+                acc = fmaf(xq[4 * c4 + 1], v.y, acc);
+                acc = fmaf(xq[4 * c4 + 2], v.z, acc);
+                acc = fmaf(xq[4 * c4 + 3], v.w, acc);
+            }
+            const float nj = __ldg(sqnorm + cloud0 + j);
+            float d = diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * acc), nj) : __fadd_rn(__fsub_rn(nj, 2.0f * acc), qq);
+            if (diag_zero && j == q) d = 0.f;
+            ex[h] = d;
+        }
+    }
+    // rank of every ambiguous entry among the ambiguous ones by exact (distance, index)
+    int rank[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) rank[h] = 0;
+    for (int src = 0; src < 32 * H; ++src) {
+        const int sh = src >> 5, sl = src & 31;
+        const float xd = __shfl_sync(FS_FULL_MASK, sh ? ex[H - 1] : ex[0], sl);
+        const int xj = __shfl_sync(FS_FULL_MASK, sh ? sj[H - 1] : sj[0], sl);
+        const bool xa = __shfl_sync(FS_FULL_MASK, (int)(sh ? amb[H - 1] : amb[0]), sl) != 0;
+        if (xa) {
+#pragma unroll
+            for (int h = 0; h < H; ++h)
+                if (amb[h] && fs_pair_less(xd, xj, ex[h], sj[h])) ++rank[h];
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const int r = h * 32 + lane;
+        int pos = -1;
+        if (in_[h]) pos = r;                                   // sure-in entries occupy ranks [0, n_in)
+        else if (amb[h] && rank[h] < slots) pos = n_in + rank[h];
+        if (pos >= skip && pos < kk) out[pos - skip] = sj[h];
+    }
+}
+
 __global__ void __launch_bounds__(256)
 knn_tc_finalize_kernel(const float* __restrict__ x, int ldx, int N, long long P, int k, int self_loop, int diag_zero,
                        const int32_t* __restrict__ cand_j, const float* __restrict__ cand_d,
@@ -423,93 +618,15 @@ knn_tc_finalize_kernel(const float* __restrict__ x, int ldx, int N, long long P,
         return;
     }
     if (lane == 0) redo[row] = 0;
-
-    FsWarpSelect<2> sel;
-    sel.init(qd_all + warp * 64, qi_all + warp * 64, 64);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int slot = h * 32 + lane;
-        const bool valid = slot < n;
-        const float d = valid ? __ldg(cand_d + row * TC_CAP + slot) : INFINITY;
-        const int j = valid ? __ldg(cand_j + row * TC_CAP + slot) : FS_IDX_PAD;
-        sel.offer(d, j, valid);
-    }
-    sel.finish();
-    float thr; int thr_j;
-    sel.get(kk - 1, thr, thr_j);
     const float cmax = __int_as_float(__ldg(norm_max_bits + 2 * b)), rmax = __int_as_float(__ldg(norm_max_bits + 2 * b + 1));
     const float qq = __ldg(sqnorm + row);
     const float err = tc_row_err(__ldg(cnorm + row), cmax, qq, rmax);
-    const float lo = thr - 2.f * err, hi = thr + 2.f * err;
-
-    bool in_[2], amb[2];
-    int n_in = 0, n_amb = 0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const bool valid = sel.i[h] != FS_IDX_PAD;
-        in_[h] = valid && sel.d[h] < lo;
-        amb[h] = valid && !in_[h] && sel.d[h] <= hi;
-        n_in += __popc(__ballot_sync(FS_FULL_MASK, in_[h]));
-        n_amb += __popc(__ballot_sync(FS_FULL_MASK, amb[h]));
-    }
-    int32_t* out = idx + row * k;
-    const int slots = kk - n_in;
-    if (n_amb == slots) {
-        // the approximation alone decides the set: ranks [0, kk) in approximate order
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int r = h * 32 + lane;
-            if (r >= skip && r < kk) out[r - skip] = sel.i[h];
-        }
-        return;
-    }
-    // ambiguous boundary: exact distances (same arithmetic as knn_feat_kernel) for the ambiguous entries
-    xq[warp][lane] = __ldg(x + row * ldx + lane);
-    xq[warp][lane + 32] = __ldg(x + row * ldx + lane + 32);
-    __syncwarp();
-    float ex[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        ex[h] = INFINITY;
-        if (amb[h]) {
-            const int j = sel.i[h];
-            const float* xr = x + (cloud0 + j) * ldx;
-            float acc = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < TC_C / 4; ++c4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + c4);
-                acc = fmaf(xq[warp][4 * c4], v.x, acc);
-                acc = fmaf(xq[warp][4 * c4 + 1], v.y, acc);
-                acc = fmaf(xq[warp][4 * c4 + 2], v.z, acc);
-                acc = fmaf(xq[warp][4 * c4 + 3], v.w, acc);
-            }
-            const float nj = __ldg(sqnorm + cloud0 + j);
-            float d = diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * acc), nj) : __fadd_rn(__fsub_rn(nj, 2.0f * acc), qq);
-            if (diag_zero && j == q) d = 0.f;
-            ex[h] = d;
-        }
-    }
-    // rank of every ambiguous entry among the ambiguous ones by exact (distance, index)
-    int rank[2] = {0, 0};
-    for (int src = 0; src < 64; ++src) {
-        const int sh = src >> 5, sl = src & 31;
-        const float sd = __shfl_sync(FS_FULL_MASK, sh ? ex[1] : ex[0], sl);
-        const int sj = __shfl_sync(FS_FULL_MASK, sh ? sel.i[1] : sel.i[0], sl);
-        const bool sa = __shfl_sync(FS_FULL_MASK, (int)(sh ? amb[1] : amb[0]), sl) != 0;
-        if (sa) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-                if (amb[h] && fs_pair_less(sd, sj, ex[h], sel.i[h])) ++rank[h];
-        }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int r = h * 32 + lane;
-        int pos = -1;
-        if (in_[h]) pos = r;                                   // sure-in entries occupy ranks [0, n_in)
-        else if (amb[h] && rank[h] < slots) pos = n_in + rank[h];
-        if (pos >= skip && pos < kk) out[pos - skip] = sel.i[h];
-    }
+    if (n <= 32)
+        tc_finalize_row<1>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, cand_j, cand_d, sqnorm, err, qq,
+                           qd_all + warp * 64, qi_all + warp * 64, xq[warp], idx + row * k);
+    else
+        tc_finalize_row<2>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, cand_j, cand_d, sqnorm, err, qq,
+                           qd_all + warp * 64, qi_all + warp * 64, xq[warp], idx + row * k);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -592,22 +709,20 @@ extern "C" int fs_knn_feat_tc(int device, fs_stream_t stream_, const float* x, i
         if (!fn || qres != cudaDriverEntryPointSuccess) return (int)cudaErrorNotSupported;
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    CUtensorMap map_a, map_b;
-    int e = make_operand_map(encode, &map_a, A, P, TC_M);
-    if (e) return e;
-    e = make_operand_map(encode, &map_b, Bm, P, TC_NB);
+    CUtensorMap map_b;
+    int e = make_operand_map(encode, &map_b, Bm, P, TC_NB);
     if (e) return e;
 
     // 1. prep
     FS_CUDA_TRY(cudaMemsetAsync(sums, 0, align_up((size_t)B * TC_C * 4, 256) + (size_t)B * 8, stream));
     tc_colsum_kernel<<<dim3(16, B), 256, 0, stream>>>(x, ldx, N, sums);
-    tc_split_kernel<<<fs_div_up(P, 8), 256, 0, stream>>>(x, ldx, P, N, sums, A, Bm, cnorm, sqnorm, nmax);
+    tc_split_kernel<<<fs_div_up(P, 8 * TC_SPLIT_ROWS), 256, 0, stream>>>(x, ldx, P, N, sums, A, Bm, cnorm, sqnorm, nmax);
     FS_RETURN_IF_LAUNCH_FAILED();
 
     // 2. tensor-core sweeps
     FS_CUDA_TRY(cudaFuncSetAttribute(knn_tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     dim3 grid(fs_div_up(N, TC_QT * TC_M), B);
-    knn_tc_select_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map_a, map_b, N, kk, diag_zero, cnorm, sqnorm, nmax,
+    knn_tc_select_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(A, P, map_b, N, kk, diag_zero, cnorm, sqnorm, nmax,
                                                                       cand_j, cand_d, cand_n);
     FS_RETURN_IF_LAUNCH_FAILED();
 
