@@ -145,7 +145,6 @@ knn3d_regs_kernel(const float* __restrict__ coords, long long batch_stride, long
 
     float* hd = hd_all + warp * CAP;
     int* hi = hi_all + warp * CAP;
-    int* hn = hn_all + warp;
     FsWarpSelect<KPL> sel;
 
     for (int r = 0; r < KNN3R_QPW; ++r) {
@@ -173,18 +172,25 @@ knn3d_regs_kernel(const float* __restrict__ coords, long long batch_stride, long
         sel.finish();
         float tau; int tj;
         sel.get(kk - 1, tau, tj);
-        // collect survivors
-        if (lane == 0) *hn = 0;
-        __syncwarp();
+        // collect survivors without atomics: per-lane hit count, exclusive scan over the lanes, private writes
+        int mine = 0;
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-            if (dist[i] <= tau) {
-                const int pos = atomicAdd(hn, 1);
-                if (pos < CAP) { hd[pos] = dist[i]; hi[pos] = i * 32 + lane; }
+        for (int i = 0; i < NPL; ++i) mine += (dist[i] <= tau) ? 1 : 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FS_FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int n = __shfl_sync(FS_FULL_MASK, incl, 31);
+        if (n <= CAP) {
+            int pos = incl - mine;
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+                if (dist[i] <= tau) { hd[pos] = dist[i]; hi[pos] = i * 32 + lane; ++pos; }
             }
         }
         __syncwarp();
-        const int n = *hn;
         sel.init(qd_all + warp * 64, qi_all + warp * 64, kk);
         if (n <= CAP && tau < INFINITY) {
             for (int base = 0; base < n; base += 32) {

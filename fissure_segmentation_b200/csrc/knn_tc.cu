@@ -46,7 +46,7 @@ constexpr int TC_WARP_TMA = TC_EPI_WARPS;
 constexpr int TC_WARP_MMA = TC_EPI_WARPS + 1;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr int TC_STAGE_BYTES = 32 * 32 * 4;  // per-warp staging of one 32 x 32 score block (sweep 2)
-constexpr int TC_CAP = 64;         // survivor slots per query
+constexpr int TC_CAP = 128;        // survivor slots per query (observed: mean 26-33, max 68)
 constexpr int TC_NCLS = 32;        // interleaved column classes of sweep 1
 constexpr int TC_MAX_KK = 24;      // kk-th smallest of 32 class minima stays near rank 1.6 kk up to here
 constexpr int TC_TMEM_ACC0 = 256;     // accumulators at columns [256, 512), A operands at [0, 2*104)
@@ -505,10 +505,10 @@ __device__ __forceinline__ void tc_finalize_row(const float* __restrict__ x, int
         sj[0] = valid ? __ldg(cand_j + row * TC_CAP + lane) : FS_IDX_PAD;
         fs_warp_bitonic_sort(sd[0], sj[0], lane);
     } else {
-        FsWarpSelect<2> sel;
-        sel.init(qd, qi, 64);
+        FsWarpSelect<H> sel;
+        sel.init(qd, qi, 32 * H);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < H; ++h) {
             const int slot = h * 32 + lane;
             const bool valid = slot < n;
             sel.offer(valid ? __ldg(cand_d + row * TC_CAP + slot) : INFINITY, valid ? __ldg(cand_j + row * TC_CAP + slot) : FS_IDX_PAD, valid);
@@ -518,11 +518,8 @@ __device__ __forceinline__ void tc_finalize_row(const float* __restrict__ x, int
         for (int h = 0; h < H; ++h) { sd[h] = sel.d[h]; sj[h] = sel.i[h]; }
     }
     const int r_thr = kk - 1;
-    float thr = __shfl_sync(FS_FULL_MASK, sd[0], r_thr & 31);
-    if (H == 2) {
-        const float t1 = __shfl_sync(FS_FULL_MASK, sd[H - 1], r_thr & 31);
-        thr = (r_thr >> 5) ? t1 : thr;
-    }
+    // kk <= 24 < 32: the kk-th smallest always sits in slot 0 of the ascending order
+    const float thr = __shfl_sync(FS_FULL_MASK, sd[0], r_thr & 31);
     const float lo = thr - 2.f * err, hi = thr + 2.f * err;
     bool in_[H], amb[H];
     int n_in = 0, n_amb = 0;
@@ -574,15 +571,18 @@ __device__ __forceinline__ void tc_finalize_row(const float* __restrict__ x, int
     int rank[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) rank[h] = 0;
-    for (int src = 0; src < 32 * H; ++src) {
-        const int sh = src >> 5, sl = src & 31;
-        const float xd = __shfl_sync(FS_FULL_MASK, sh ? ex[H - 1] : ex[0], sl);
-        const int xj = __shfl_sync(FS_FULL_MASK, sh ? sj[H - 1] : sj[0], sl);
-        const bool xa = __shfl_sync(FS_FULL_MASK, (int)(sh ? amb[H - 1] : amb[0]), sl) != 0;
-        if (xa) {
 #pragma unroll
-            for (int h = 0; h < H; ++h)
-                if (amb[h] && fs_pair_less(xd, xj, ex[h], sj[h])) ++rank[h];
+    for (int sh = 0; sh < H; ++sh) {
+        if (!__any_sync(FS_FULL_MASK, amb[sh])) continue;
+        for (int sl = 0; sl < 32; ++sl) {
+            const float xd = __shfl_sync(FS_FULL_MASK, ex[sh], sl);
+            const int xj = __shfl_sync(FS_FULL_MASK, sj[sh], sl);
+            const bool xa = __shfl_sync(FS_FULL_MASK, (int)amb[sh], sl) != 0;
+            if (xa) {
+#pragma unroll
+                for (int h = 0; h < H; ++h)
+                    if (amb[h] && fs_pair_less(xd, xj, ex[h], sj[h])) ++rank[h];
+            }
         }
     }
 #pragma unroll
@@ -624,8 +624,11 @@ knn_tc_finalize_kernel(const float* __restrict__ x, int ldx, int N, long long P,
     if (n <= 32)
         tc_finalize_row<1>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, cand_j, cand_d, sqnorm, err, qq,
                            qd_all + warp * 64, qi_all + warp * 64, xq[warp], idx + row * k);
-    else
+    else if (n <= 64)
         tc_finalize_row<2>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, cand_j, cand_d, sqnorm, err, qq,
+                           qd_all + warp * 64, qi_all + warp * 64, xq[warp], idx + row * k);
+    else
+        tc_finalize_row<4>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, cand_j, cand_d, sqnorm, err, qq,
                            qd_all + warp * 64, qi_all + warp * 64, xq[warp], idx + row * k);
 }
 

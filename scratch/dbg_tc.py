@@ -24,7 +24,7 @@ for kind in ("randn", "smooth"):
     idx = torch.full((B, N, k), -1, dtype=torch.int32, device='cuda')
     _lib.call("fs_knn_feat_tc", feat, feat, 64, B, N, 64, k, int(sl), 1, idx, None, ws, nbytes)
     torch.cuda.synchronize()
-    off_n = 2 * al(P * 512) + 2 * al(P * 256)
+    off_n = 2 * al(P * 512) + 2 * al(P * 512)
     cnt = ws[off_n:off_n + 4 * P].view(torch.int32)
     off_redo = off_n + 3 * al(P * 4) + al(B * 256) + al(B * 8)
     redo = ws[off_redo:off_redo + P]
