@@ -176,6 +176,12 @@ class EdgeConv(nn.Module):
         if Cp not in FUSED_WIDTHS:
             raise NotImplementedError(f"fused EdgeConv supports widths {FUSED_WIDTHS}, got {Cp}")
         C = x_pm.shape[1]
+        if (len(self.shared_mlp) > 1 and C == 3 and Cp in (64, 128) and not x_pm.requires_grad
+                and first.norm is not None and first.has_activation and abs(first.negative_slope - 0.2) < 1e-12):
+            # first layer on raw coordinates: batch statistics from the moments of the 6-D edge vectors, H written
+            # once, weight gradient accumulated straight from dH (csrc/edge3.cu)
+            h = ops.edge_first3(x_pm.float().contiguous(), first.conv.weight, first.norm, graph, cdt)
+            return self._finish_multilayer(h, graph)
         w = first.weight_matrix()
         w_cat = torch.cat([w[:, :C], w[:, C:] - w[:, :C]], dim=0)             # [W1 ; W2 - W1]  (2Cp, C)
         # The per-point table stays fp32 in every precision mode: y = a_j + b_i = W1 (x_j - x_i) + W2 x_i
@@ -189,6 +195,10 @@ class EdgeConv(nn.Module):
         # two (or more) layers: layer 1 pre-activations as an edge tensor (compute dtype), middle layers in
         # torch, last layer's BatchNorm + LeakyReLU + max over k in one reduction kernel
         h = first.norm_act_pm(ops.edge_build(table, graph, cdt))
+        return self._finish_multilayer(h, graph)
+
+    def _finish_multilayer(self, h, graph):
+        """Layers 2.. of a multi-layer EdgeConv on the hidden edge tensor h (P*k, C1), then max over k."""
         for layer in self.shared_mlp[1:-1]:
             h = layer.forward_pm(h)
         last = self.shared_mlp[-1]

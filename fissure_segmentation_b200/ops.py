@@ -454,3 +454,58 @@ class _TableGemmFn(torch.autograd.Function):
 
 def table_gemm(x, w):
     return _TableGemmFn.apply(x, w)
+
+
+# ------------------------------------------------------------------------------------------- first layer, 3-D input
+
+class _EdgeFirst3Fn(torch.autograd.Function):
+    """H = LeakyReLU(BatchNorm2d(Conv2d(6 -> Cp)([x_j - x_i, x_i]))) for a 3-channel input x (P, 3): first shared
+    layer of a multi-layer EdgeConv on coordinates (models/dgcnn.py:119, 251). Batch statistics come from the
+    moments of the 6-D edge vectors; H (P*k, Cp) is the only tensor written, the weight gradient is accumulated
+    directly from dH (no scatter, x gets no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, graph, running_mean, running_var, nbt, training, eps, momentum, out_dtype):
+        B, N, k = graph.B, graph.N, graph.k
+        Cp = w.shape[0]
+        dev = x.device
+        w32 = w.detach().reshape(Cp, 6).float().contiguous()
+        gamma32, beta32 = gamma.detach().float(), beta.detach().float()
+        coef = torch.empty(4 * Cp, dtype=torch.float32, device=dev)
+        mom = None
+        if training:
+            mom = torch.zeros(_lib.load().fs_edge3_moment_doubles(), dtype=torch.float64, device=dev)
+            _lib.call("fs_edge3_bn_coef", x, x, x.stride(0), graph.idx, B, N, k, w32, Cp, gamma32, beta32, eps, momentum,
+                      mom, coef, running_mean, running_var, nbt)
+        else:
+            _lib.call("fs_bn_coef_eval", x, Cp, gamma32, beta32, running_mean, running_var, eps, coef)
+        h = torch.empty(B * N * k, Cp, dtype=out_dtype, device=dev)
+        _lib.call("fs_edge3_hidden", x, x, x.stride(0), graph.idx, B, N, k, w32, Cp, coef, h, _lib.dtype_code(h))
+        ctx.graph, ctx.training = graph, training
+        ctx.w_shape = w.shape
+        ctx.save_for_backward(x, w32, coef, mom)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, w32, coef, mom = ctx.saved_tensors
+        graph = ctx.graph
+        B, N, k = graph.B, graph.N, graph.k
+        Cp = w32.shape[0]
+        if dh.dtype not in (torch.float32, torch.bfloat16):
+            dh = dh.float()
+        dh = dh.contiguous()
+        dgb = _stats_buffer(Cp, x.device)
+        acc = torch.zeros(Cp, 6, dtype=torch.float32, device=x.device)
+        dw = torch.empty(Cp, 6, dtype=torch.float32, device=x.device)
+        _lib.call("fs_edge3_bwd", x, x, x.stride(0), graph.idx, B, N, k, w32, Cp, coef, dh, _lib.dtype_code(dh),
+                  int(ctx.training), mom, dgb, acc, dw)
+        dgb32 = dgb[:2 * Cp].float()
+        return None, dw.view(ctx.w_shape), dgb32[Cp:], dgb32[:Cp], None, None, None, None, None, None, None, None
+
+
+def edge_first3(x, conv_weight, bn, graph, out_dtype):
+    """x (P, >=3) fp32 point-major (first three channels are used), conv_weight (Cp, 6, 1, 1)."""
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    return _EdgeFirst3Fn.apply(x, conv_weight, bn.weight, bn.bias, graph, bn.running_mean, bn.running_var,
+                               bn.num_batches_tracked, bn.training, bn.eps, bn.momentum, out_dtype)

@@ -233,6 +233,32 @@ int fs_edge_reduce_bwd(int device, fs_stream_t stream, const void* z, int z_dtyp
                        const uint8_t* arg, long long P, int k, int Cp, const float* coef,
                        const double* dgb, double count, int train_stats, void* dz, int dz_dtype);
 
+/* ---------------------------------------------------------------- first EdgeConv layer on 3-D inputs - */
+
+/*
+ * Conv2d(6 -> Cp, 1x1) + BatchNorm2d + LeakyReLU(0.2) on the edge features [x_j - x_i, x_i] of a 3-channel input
+ * (first shared layer of ec1 and of the spatial transformer's EdgeConv, models/dgcnn.py:119, 251, 15-36):
+ *   fs_edge3_bn_coef  batch statistics of all Cp channels from the 27 moments of the 6-D edge vectors
+ *                     (moments: zero-filled f64 workspace of fs_edge3_moment_doubles() entries) -> coef [4*Cp],
+ *                     running statistics updated like fs_bn_finalize
+ *   fs_edge3_hidden   H [B*N*k, Cp] (fp32 / bf16) = LeakyReLU(scale (w.e - mu) + beta)
+ *   fs_edge3_bwd      ONE pass over dH: dgb (zeroed stats buffer) = (sum d, sum d*yhat), acc_ws = sum_e d_e (x) e; the
+ *                     BatchNorm-coupled dW [Cp, 6] follows in closed form from the moments (the 3-channel input
+ *                     itself gets no gradient)
+ *   x [B*N, ldx] fp32 point-major (first 3 channels), w [Cp, 6] fp32 row-major, idx as everywhere.
+ */
+size_t fs_edge3_moment_doubles(void);
+int fs_edge3_bn_coef(int device, fs_stream_t stream, const float* x, int ldx, const int32_t* idx, int B, int N,
+                     int k, const float* w, int Cp, const float* gamma, const float* beta, float eps,
+                     float momentum, double* moments, float* coef, float* running_mean, float* running_var,
+                     long long* num_batches_tracked);
+int fs_edge3_hidden(int device, fs_stream_t stream, const float* x, int ldx, const int32_t* idx, int B, int N,
+                    int k, const float* w, int Cp, const float* coef, void* h, int h_dtype);
+int fs_edge3_bwd(int device, fs_stream_t stream, const float* x, int ldx, const int32_t* idx, int B, int N, int k,
+                 const float* w, int Cp, const float* coef, const void* dh, int dh_dtype, int train_stats,
+                 const double* moments /* from fs_edge3_bn_coef */, double* dgb,
+                 float* acc_ws /* [Cp*6] zeroed */, float* dw /* [Cp*6] out */);
+
 /* ---------------------------------------------------------------- dense layers ------------- */
 
 /*

@@ -148,3 +148,33 @@ def test_reverse_graph_is_consistent(lib):
     rev = torch.stack([tgt_of_slot, rev_src], 1)
     key = lambda t: (t[:, 0] * (B * N) + t[:, 1]).sort()[0]   # noqa: E731
     assert torch.equal(key(fwd), key(rev))
+
+
+@pytest.mark.parametrize("widths,N,k", [([64, 64], 2048, 20), ([64, 128], 700, 16)])
+def test_two_layer_edgeconv_on_coordinates_vs_oracle(lib, widths, N, k):
+    """ec1 / spatial-transformer EdgeConv on raw xyz (csrc/edge3.cu: statistics from the moments of the 6-D edge
+    vectors, weight gradient without scatter): strict layer-wise tolerances against the oracle."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from fissure_segmentation_b200 import synth
+    B = 2
+    x, _ = synth.make_batch(B, N, seed=77, jitter=True)
+    graph = O.knn(x, k, self_loop=True)
+    p = O.make_params(_shapes(6, widths), 47)
+    ec = fs.EdgeConv(3, widths, k, first_layer=True).to(DEV)
+    ec.load_state_dict(p)
+    ec.train()
+    out = ec(x.to(DEV), graph.to(DEV))
+    po = {"ec." + n: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in n else v)
+          for n, v in p.items()}
+    stats = {}
+    ref = O.edgeconv(x, po, "ec", 2, k, graph, True, True, stats)
+    assert_close(out, ref, 1e-4, 2e-5, "forward")
+    gen = torch.Generator().manual_seed(3)
+    gout = torch.randn(ref.shape, generator=gen)
+    out.backward(gout.to(DEV))
+    ref.backward(gout)
+    for n, q in ec.named_parameters():
+        assert rel_err(q.grad, po["ec." + n].grad) < 2e-4, (n, rel_err(q.grad, po["ec." + n].grad))
+    for n, v in stats.items():
+        assert_close(ec.state_dict()[n[3:]], v, 1e-4, 1e-6, n)
+    assert int(ec.state_dict()["shared_mlp.0.layers.1.num_batches_tracked"]) == 1
