@@ -139,25 +139,32 @@ edge3_hidden_kernel(const float* __restrict__ x, int ldx, const int32_t* __restr
         float base[NC];                               // contribution of x_i: w[3:6] . x_i
 #pragma unroll
         for (int i = 0; i < NC; ++i) base[i] = fmaf(wr[i][5], xi2, fmaf(wr[i][4], xi1, wr[i][3] * xi0));
-        for (int t = 0; t < k; ++t) {
-            const long long j = cloud0 + __ldg(idx + pt * k + t);
-            const float d0 = __ldg(x + j * ldx) - xi0, d1 = __ldg(x + j * ldx + 1) - xi1, d2 = __ldg(x + j * ldx + 2) - xi2;
-            float o[NC];
+        for (int t0 = 0; t0 < k; t0 += 32) {
+            // one neighbour per lane: all index / coordinate gathers of the point are in flight together
+            const int tl = t0 + lane < k ? t0 + lane : k - 1;
+            const long long jl = cloud0 + __ldg(idx + pt * k + tl);
+            const float n0 = __ldg(x + jl * ldx), n1 = __ldg(x + jl * ldx + 1), n2 = __ldg(x + jl * ldx + 2);
+            const int tn = k - t0 < 32 ? k - t0 : 32;
+            for (int tt = 0; tt < tn; ++tt) {
+                const float d0 = __shfl_sync(FS_FULL_MASK, n0, tt) - xi0, d1 = __shfl_sync(FS_FULL_MASK, n1, tt) - xi1,
+                            d2 = __shfl_sync(FS_FULL_MASK, n2, tt) - xi2;
+                float o[NC];
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                const float y = fmaf(wr[i][2], d2, fmaf(wr[i][1], d1, fmaf(wr[i][0], d0, base[i])));
-                o[i] = fs_leaky(fmaf(sc[i], y - mu[i], be[i]));
-            }
-            const long long eo = (pt * k + t) * CP + c0;
-            if (sizeof(HT) == 2) {
-                __nv_bfloat162 v[NC / 2];
+                for (int i = 0; i < NC; ++i) {
+                    const float y = fmaf(wr[i][2], d2, fmaf(wr[i][1], d1, fmaf(wr[i][0], d0, base[i])));
+                    o[i] = fs_leaky(fmaf(sc[i], y - mu[i], be[i]));
+                }
+                const long long eo = (pt * k + t0 + tt) * CP + c0;
+                if (sizeof(HT) == 2) {
+                    __nv_bfloat162 v[NC / 2];
 #pragma unroll
-                for (int i = 0; i < NC / 2; ++i) v[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-                if (NC == 2) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(h) + eo) = v[0];
-                else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(h) + eo) = *reinterpret_cast<uint2*>(v);
-            } else {
-                if (NC == 2) *reinterpret_cast<float2*>(reinterpret_cast<float*>(h) + eo) = make_float2(o[0], o[1]);
-                else *reinterpret_cast<float4*>(reinterpret_cast<float*>(h) + eo) = make_float4(o[0], o[1], o[NC - 2], o[NC - 1]);
+                    for (int i = 0; i < NC / 2; ++i) v[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+                    if (NC == 2) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(h) + eo) = v[0];
+                    else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(h) + eo) = *reinterpret_cast<uint2*>(v);
+                } else {
+                    if (NC == 2) *reinterpret_cast<float2*>(reinterpret_cast<float*>(h) + eo) = make_float2(o[0], o[1]);
+                    else *reinterpret_cast<float4*>(reinterpret_cast<float*>(h) + eo) = make_float4(o[0], o[1], o[NC - 2], o[NC - 1]);
+                }
             }
         }
     }
@@ -215,20 +222,36 @@ edge3_bwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict
         float base[NC], dsum[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) { base[i] = fmaf(wr[i][5], xi2, fmaf(wr[i][4], xi1, wr[i][3] * xi0)); dsum[i] = 0.f; }
-        for (int t = 0; t < k; ++t) {
-            const long long j = cloud0 + __ldg(idx + pt * k + t);
-            const float d0 = __ldg(x + j * ldx) - xi0, d1 = __ldg(x + j * ldx + 1) - xi1, d2 = __ldg(x + j * ldx + 2) - xi2;
-            float g[NC];
-            load_nc<GT, NC>(dh + (pt * k + t) * CP + c0, g);
+        for (int t0 = 0; t0 < k; t0 += 32) {
+            const int tl = t0 + lane < k ? t0 + lane : k - 1;
+            const long long jl = cloud0 + __ldg(idx + pt * k + tl);
+            const float n0 = __ldg(x + jl * ldx), n1 = __ldg(x + jl * ldx + 1), n2 = __ldg(x + jl * ldx + 2);
+            const int tn = k - t0 < 32 ? k - t0 : 32;
+            for (int tb = 0; tb < tn; tb += 4) {
+                float g[4][NC];
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                const float y = fmaf(wr[i][2], d2, fmaf(wr[i][1], d1, fmaf(wr[i][0], d0, base[i])));
-                const float yc = y - mu[i];
-                const float z = fmaf(sc[i], yc, be[i]);
-                const float d = z > 0.f ? g[i] : 0.2f * g[i];
-                s2[i] = fmaf(d, yc * inv[i], s2[i]);
-                dsum[i] += d;
-                A[i][0] = fmaf(d, d0, A[i][0]); A[i][1] = fmaf(d, d1, A[i][1]); A[i][2] = fmaf(d, d2, A[i][2]);
+                for (int u = 0; u < 4; ++u) {       // four independent dH row loads in flight
+                    const int tt = tb + u < tn ? tb + u : tn - 1;
+                    load_nc<GT, NC>(dh + (pt * k + t0 + tt) * CP + c0, g[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (tb + u < tn) {
+                        const int tt = tb + u;
+                        const float d0 = __shfl_sync(FS_FULL_MASK, n0, tt) - xi0, d1 = __shfl_sync(FS_FULL_MASK, n1, tt) - xi1,
+                                    d2 = __shfl_sync(FS_FULL_MASK, n2, tt) - xi2;
+#pragma unroll
+                        for (int i = 0; i < NC; ++i) {
+                            const float y = fmaf(wr[i][2], d2, fmaf(wr[i][1], d1, fmaf(wr[i][0], d0, base[i])));
+                            const float yc = y - mu[i];
+                            const float z = fmaf(sc[i], yc, be[i]);
+                            const float d = z > 0.f ? g[u][i] : 0.2f * g[u][i];
+                            s2[i] = fmaf(d, yc * inv[i], s2[i]);
+                            dsum[i] += d;
+                            A[i][0] = fmaf(d, d0, A[i][0]); A[i][1] = fmaf(d, d1, A[i][1]); A[i][2] = fmaf(d, d2, A[i][2]);
+                        }
+                    }
+                }
             }
         }
 #pragma unroll
