@@ -251,54 +251,94 @@ bn_act_bwd_apply_kernel(const GT* __restrict__ g, int ldg, const T* __restrict__
     }
 }
 
-// Global max-pool fused with the statistics: per cloud and channel, max (gamma >= 0) or min (gamma < 0) of x over the
-// N rows, its row index, and the column sums. grid = (C / 64, B); block = 4 row-groups x 64 channels.
+// Global max-pool fused with the statistics. grid = (chunks, B): each block scans a chunk of the N rows of one cloud
+// for all C channels (128-bit loads, four rows in flight per thread), keeps max of the sign-flipped key (so that
+// gamma < 0 channels take the minimum) with its row, and publishes (key, row) per channel with one 64-bit atomicMax;
+// ties go to the lower row like a sequential arg-max. Column statistics go through fs_stats_commit.
+__device__ __forceinline__ unsigned int ordered_u32(float f) {
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_u32(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DN_THREADS)
 pool_reduce_kernel(const T* __restrict__ x, int ld, int N, int C, const float* __restrict__ gamma,
-                   float* __restrict__ sel, int32_t* __restrict__ arg, double* __restrict__ stats) {
-    __shared__ float s_best[4][64];
-    __shared__ int s_arg[4][64];
-    __shared__ float s_1[4][64], s_2[4][64];
+                   unsigned long long* __restrict__ packed, double* __restrict__ stats) {
+    constexpr int V = Vec<T>::N;
+    extern __shared__ double red[];     // [2 * V * DN_THREADS]
+    RowMap m(C, V);
+    const int cc = m.c0;
     const int b = blockIdx.y;
-    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int rg = threadIdx.x >> 6;
-    const bool use_max = __ldg(gamma + c) >= 0.f;
-    const T* xb = x + (long long)b * N * ld + c;
-    const float piv = stats ? (float)x[c] : 0.f;        // row 0 of the whole table
-    float best = use_max ? -INFINITY : INFINITY;
-    int barg = 0;
-    float f1 = 0.f, f2 = 0.f;
-    for (int r = rg; r < N; r += 4) {
-        const float v = (float)xb[(long long)r * ld];
-        const bool better = use_max ? (v > best) : (v < best);
-        if (better) { best = v; barg = r; }
-        const float d = v - piv;
-        f1 += d;
-        f2 = fmaf(d, d, f2);
-    }
-    s_best[rg][threadIdx.x & 63] = best; s_arg[rg][threadIdx.x & 63] = barg;
-    s_1[rg][threadIdx.x & 63] = f1; s_2[rg][threadIdx.x & 63] = f2;
-    __syncthreads();
-    if (rg == 0) {
-        const int t = threadIdx.x;
-        double a1 = 0.0, a2 = 0.0;
+    const int rows_per_chunk = (N + gridDim.x - 1) / gridDim.x;
+    const int r_begin = blockIdx.x * rows_per_chunk;
+    const int r_end = min(N, r_begin + rows_per_chunk);
+    const T* xb = x + (long long)b * N * ld + cc;
+    unsigned int flip[V];
+    float piv[V], f1[V], f2[V], best[V];
+    int barg[V];
+    {
+        float p0[V];
+        Vec<T>::load(x + cc, p0);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const float v = s_best[g][t];
-            const int a = s_arg[g][t];
-            const bool better = use_max ? (v > best || (v == best && a < barg)) : (v < best || (v == best && a < barg));
-            if (g > 0 && better) { best = v; barg = a; }
-            a1 += (double)s_1[g][t]; a2 += (double)s_2[g][t];
-        }
-        sel[(long long)b * C + c] = best;
-        arg[(long long)b * C + c] = barg;
-        if (stats) {
-            atomicAdd(&stats[c], a1);
-            atomicAdd(&stats[C + c], a2);
-            if (b == 0) stats[2 * C + c] = (double)piv;
+        for (int i = 0; i < V; ++i) {
+            flip[i] = __ldg(gamma + cc + i) >= 0.f ? 0u : 0x80000000u;
+            piv[i] = stats ? p0[i] : 0.f; f1[i] = 0.f; f2[i] = 0.f; best[i] = -INFINITY; barg[i] = 0x7fffffff;
         }
     }
+    const int step = m.rows_per_pass;
+    int r = r_begin + m.r;
+    for (; r < r_end; r += 4 * step) {
+        float f[4][V];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Vec<T>::load(xb + (long long)min(r + u * step, r_end - 1) * ld, f[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (r + u * step < r_end) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float key = __uint_as_float(__float_as_uint(f[u][i]) ^ flip[i]);
+                    const bool better = key > best[i];
+                    best[i] = better ? key : best[i];
+                    barg[i] = better ? r + u * step : barg[i];
+                    const float d = f[u][i] - piv[i];
+                    f1[i] += d;
+                    f2[i] = fmaf(d, d, f2[i]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        if (barg[i] != 0x7fffffff) {
+            const unsigned long long pk = ((unsigned long long)ordered_u32(best[i]) << 32) | (unsigned long long)(0xffffffffu - (unsigned)barg[i]);
+            atomicMax(packed + (long long)b * C + cc + i, pk);
+        }
+    }
+    if (stats) {
+        double d1[V], d2[V];
+        int chans[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) { d1[i] = (double)f1[i]; d2[i] = (double)f2[i]; chans[i] = cc + i; }
+        // the grid is 2-D: fold it so that the ticket logic of fs_stats_commit sees one linear block index
+        fs_stats_commit_2d<V>(red, d1, d2, chans, m.tpr, C, stats);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && m.r == 0) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) stats[2 * C + cc + i] = (double)piv[i];
+        }
+    }
+}
+
+__global__ void pool_decode_kernel(const unsigned long long* __restrict__ packed, const float* __restrict__ gamma, int C,
+                                   long long total, float* __restrict__ sel, int32_t* __restrict__ arg) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const unsigned long long pk = packed[e];
+    const unsigned int flip = __ldg(gamma + (int)(e % C)) >= 0.f ? 0u : 0x80000000u;
+    sel[e] = __uint_as_float(__float_as_uint(from_ordered_u32((unsigned int)(pk >> 32))) ^ flip);
+    arg[e] = (int32_t)(0xffffffffu - (unsigned int)(pk & 0xffffffffu));
 }
 
 // dX[r, c] = scale * ( [r == arg[b,c]] * d[b,c] - dbeta/M - xhat[r,c] * dgamma/M ),  d = g * LeakyReLU'(z_sel)
@@ -307,47 +347,50 @@ __global__ void __launch_bounds__(DN_THREADS)
 pool_bwd_kernel(const T* __restrict__ x, int ld, int N, long long rows, int C, const float* __restrict__ g,
                 const float* __restrict__ sel, const int32_t* __restrict__ arg, const float* __restrict__ coef, float slope,
                 const double* __restrict__ dgb, double count, int train_stats, OT* __restrict__ dx, int ld_dx) {
-    constexpr int V = 4;
+    constexpr int V = Vec<T>::N;
     RowMap m(C, V);
-    for (int cc = m.c0; cc < C; cc += m.tpr * V) {
-        float mu[V], inv[V], sc[V], be[V], mb[V], mg[V];
+    const int cc = m.c0;
+    float mu[V], sc[V], mb[V], mg[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            mu[i] = __ldg(coef + cc + i); inv[i] = __ldg(coef + C + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i);
-            be[i] = __ldg(coef + 3 * C + cc + i);
-            mb[i] = train_stats ? (float)(dgb[cc + i] / count) : 0.f;
-            mg[i] = train_stats ? (float)(dgb[C + cc + i] / count) * inv[i] : 0.f;
-        }
-        for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += (long long)gridDim.x * m.rows_per_pass) {
-            const long long b = row / N;
-            const int r = (int)(row - b * N);
-            float f[V], o[V];
-            if (sizeof(T) == 4) Vec<float>::load(reinterpret_cast<const float*>(x) + row * ld + cc, f);
-            else {
-                uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + row * ld + cc));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-                float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
-                f[0] = a.x; f[1] = a.y; f[2] = b2.x; f[3] = b2.y;
-            }
-            const int4 av = __ldg(reinterpret_cast<const int4*>(arg + b * C + cc));
-            const int ar[4] = {av.x, av.y, av.z, av.w};
+    for (int i = 0; i < V; ++i) {
+        mu[i] = __ldg(coef + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i);
+        mb[i] = train_stats ? (float)(dgb[cc + i] / count) : 0.f;
+        mg[i] = train_stats ? (float)(dgb[C + cc + i] / count) * __ldg(coef + C + cc + i) : 0.f;
+    }
+    const long long step = (long long)gridDim.x * m.rows_per_pass;
+    for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += 2 * step) {
+        float f[2][V];
+        const bool two = row + step < rows;
+        Vec<T>::load(x + row * ld + cc, f[0]);
+        if (two) Vec<T>::load(x + (row + step) * ld + cc, f[1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const long long rr = row + u * step;
+            const long long b = rr / N;
+            const int r = (int)(rr - b * N);
+            float o[V];
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 float routed = 0.f;
-                if (ar[i] == r) {
-                    const float zs = fmaf(sc[i], __ldg(sel + b * C + cc + i) - mu[i], be[i]);
+                if (__ldg(arg + b * C + cc + i) == r) {
+                    const float zs = fmaf(sc[i], __ldg(sel + b * C + cc + i) - mu[i], __ldg(coef + 3 * C + cc + i));
                     const float gv = __ldg(g + b * C + cc + i);
                     routed = zs > 0.f ? gv : slope * gv;
                 }
-                o[i] = train_stats ? sc[i] * (routed - mb[i] - mg[i] * (f[i] - mu[i])) : sc[i] * routed;
+                o[i] = train_stats ? sc[i] * (routed - mb[i] - mg[i] * (f[u][i] - mu[i])) : sc[i] * routed;
             }
-            if (sizeof(OT) == 4) Vec<float>::store(reinterpret_cast<float*>(dx) + row * ld_dx + cc, o);
-            else {
+            if (V == 8 && sizeof(OT) == 4) {
+                Vec<float>::store(reinterpret_cast<float*>(dx) + rr * ld_dx + cc, o);
+                Vec<float>::store(reinterpret_cast<float*>(dx) + rr * ld_dx + cc + 4, o + 4);
+            } else if (V == 4 && sizeof(OT) == 2) {
                 uint2 v;
                 __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
                 h[0] = __floats2bfloat162_rn(o[0], o[1]);
                 h[1] = __floats2bfloat162_rn(o[2], o[3]);
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dx) + row * ld_dx + cc) = v;
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dx) + rr * ld_dx + cc) = v;
+            } else {
+                Vec<OT>::store(dx + rr * ld_dx + cc, o);
             }
         }
     }
@@ -430,14 +473,23 @@ extern "C" int fs_bn_act_bwd(int device, fs_stream_t stream_, const void* g, int
 }
 
 extern "C" int fs_pool_reduce(int device, fs_stream_t stream_, const void* x, int dtype, int ld, int B, int N, int C,
-                              const float* gamma, float* sel, int32_t* arg, double* stats) {
-    if (!x || !gamma || !sel || !arg || B <= 0 || N <= 0 || ld < C) return FS_ERR_BAD_ARG;
-    if (C % 64) return FS_ERR_UNSUPPORTED;
+                              const float* gamma, float* sel, int32_t* arg, double* stats, unsigned long long* packed_ws) {
+    if (!x || !gamma || !sel || !arg || !packed_ws || B <= 0 || N <= 0 || ld < C) return FS_ERR_BAD_ARG;
+    const int vec = dtype == FS_BF16 ? 8 : 4;
+    if (!pow2_width(C, vec)) return FS_ERR_UNSUPPORTED;
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
-    dim3 grid(C / 64, B);
-    if (dtype == FS_BF16) pool_reduce_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, N, C, gamma, sel, arg, stats);
-    else pool_reduce_kernel<<<grid, 256, 0, stream>>>((const float*)x, ld, N, C, gamma, sel, arg, stats);
+    int chunks = (4 * FS_NUM_SMS + B - 1) / B;          // about four blocks per SM in total
+    const int rpp = rows_per_pass(C, vec);
+    if (chunks > (N + 4 * rpp - 1) / (4 * rpp)) chunks = (N + 4 * rpp - 1) / (4 * rpp);
+    if (chunks < 1) chunks = 1;
+    dim3 grid(chunks, B);
+    const size_t smem = (size_t)2 * vec * DN_THREADS * sizeof(double);
+    if (dtype == FS_BF16) pool_reduce_kernel<<<grid, DN_THREADS, smem, stream>>>((const __nv_bfloat16*)x, ld, N, C, gamma, packed_ws, stats);
+    else pool_reduce_kernel<<<grid, DN_THREADS, smem, stream>>>((const float*)x, ld, N, C, gamma, packed_ws, stats);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    const long long total = (long long)B * C;
+    pool_decode_kernel<<<fs_div_up(total, 256), 256, 0, stream>>>(packed_ws, gamma, C, total, sel, arg);
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
 }
@@ -447,11 +499,12 @@ extern "C" int fs_pool_bwd(int device, fs_stream_t stream_, const void* x, int d
                            const double* dgb, double count, int train_stats, void* dx, int dx_dtype, int ld_dx) {
     if (!x || !g || !sel || !arg || !coef || !dx || B <= 0 || N <= 0 || ld < C || ld_dx < C) return FS_ERR_BAD_ARG;
     if (train_stats && (!dgb || count <= 0)) return FS_ERR_BAD_ARG;
-    if (!pow2_width(C, 4)) return FS_ERR_UNSUPPORTED;
+    const int vec = dtype == FS_BF16 ? 8 : 4;
+    if (!pow2_width(C, vec)) return FS_ERR_UNSUPPORTED;
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long rows = (long long)B * N;
-    const int grid = dn_grid(rows, rows_per_pass(C, 4));
+    const int grid = dn_grid(rows, rows_per_pass(C, vec));
 #define GO(T, OT) pool_bwd_kernel<<<grid, DN_THREADS, 0, stream>>>((const T*)x, ld, N, rows, C, g, sel, arg, coef, slope, dgb, count, train_stats, (OT*)dx, ld_dx)
     if (dtype == FS_BF16 && dx_dtype == FS_BF16) GO(__nv_bfloat16, __nv_bfloat16);
     else if (dtype == FS_BF16) GO(__nv_bfloat16, float);

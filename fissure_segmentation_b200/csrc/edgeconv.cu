@@ -544,57 +544,75 @@ edge_build_bwd_kernel(const YT* __restrict__ dy, const int32_t* __restrict__ idx
     }
 }
 
+// 128-bit row segments: VEC = 4 channels (fp32) or 8 channels (bf16) per thread, four rows in flight per thread.
 template <typename ZT, int CP>
 __global__ void __launch_bounds__(256)
 edge_reduce_kernel(const ZT* __restrict__ z, long long P, int k, const float* __restrict__ gamma,
                    float* __restrict__ sel, uint8_t* __restrict__ arg, float* __restrict__ sy, double* __restrict__ stats) {
-    constexpr int Q = CP / 4;
+    constexpr int V = FsRow<ZT>::VEC;
+    constexpr int Q = CP / V;              // threads per point
     constexpr int ROWS = 256 / Q;
-    __shared__ double red[2 * 4 * 256];
+    __shared__ double red[2 * V * 256];
     const int l = threadIdx.x % Q;
     const int r = threadIdx.x / Q;
-    const int c0 = l * 4;
-    bool use_max[4];
-    float pivot[4];
+    const int c0 = l * V;
+    uint32_t flip[V];
+    float pivot[V];
     {
-        float z0[4];
-        load4(z + c0, z0);
+        float z0[V];
+        FsRow<ZT>::load(z + c0, z0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { use_max[i] = __ldg(gamma + c0 + i) >= 0.f; pivot[i] = stats ? z0[i] : 0.f; }
+        for (int i = 0; i < V; ++i) { flip[i] = __ldg(gamma + c0 + i) >= 0.f ? 0u : 0x80000000u; pivot[i] = stats ? z0[i] : 0.f; }
     }
-    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float t1[V], t2[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { t1[i] = 0.f; t2[i] = 0.f; }
     for (long long pt = (long long)blockIdx.x * ROWS + r; pt < P; pt += (long long)gridDim.x * ROWS) {
-        float best[4], ysum[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
-        int barg[4] = {0, 0, 0, 0};
+        float best[V], ysum[V], f1[V], f2[V];
+        int barg[V];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) best[i] = use_max[i] ? -INFINITY : INFINITY;
-        for (int t = 0; t < k; ++t) {
-            float zv[4];
-            load4(z + (pt * k + t) * CP + c0, zv);
+        for (int i = 0; i < V; ++i) { best[i] = -INFINITY; barg[i] = 0; ysum[i] = 0.f; f1[i] = 0.f; f2[i] = 0.f; }
+        const ZT* zp = z + pt * k * CP + c0;
+        for (int t0 = 0; t0 < k; t0 += 4) {
+            float zv[4][V];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool better = use_max[i] ? (zv[i] > best[i]) : (zv[i] < best[i]);
-                if (better) { best[i] = zv[i]; barg[i] = t; }
-                ysum[i] += zv[i];
-                const float ys = zv[i] - pivot[i];
-                f1[i] += ys;
-                f2[i] = fmaf(ys, ys, f2[i]);
+            for (int u = 0; u < 4; ++u) FsRow<ZT>::load(zp + (long long)(t0 + u < k ? t0 + u : k - 1) * CP, zv[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (t0 + u < k) {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        const float key = __uint_as_float(__float_as_uint(zv[u][i]) ^ flip[i]);
+                        const bool better = key > best[i];
+                        best[i] = better ? key : best[i];
+                        barg[i] = better ? t0 + u : barg[i];
+                        ysum[i] += zv[u][i];
+                        const float ys = zv[u][i] - pivot[i];
+                        f1[i] += ys;
+                        f2[i] = fmaf(ys, ys, f2[i]);
+                    }
+                }
             }
         }
-        store4(sel + pt * CP + c0, best);
-        if (sy) store4(sy + pt * CP + c0, ysum);
-        *reinterpret_cast<uint32_t*>(arg + pt * CP + c0) =
-            (uint32_t)barg[0] | ((uint32_t)barg[1] << 8) | ((uint32_t)barg[2] << 16) | ((uint32_t)barg[3] << 24);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { s1[i] += (double)f1[i]; s2[i] += (double)f2[i]; }
+        for (int i = 0; i < V; ++i) { best[i] = __uint_as_float(__float_as_uint(best[i]) ^ flip[i]); t1[i] += f1[i]; t2[i] += f2[i]; }
+#pragma unroll
+        for (int h = 0; h < V; h += 4) {
+            store4(sel + pt * CP + c0 + h, best + h);
+            if (sy) store4(sy + pt * CP + c0 + h, ysum + h);
+            *reinterpret_cast<uint32_t*>(arg + pt * CP + c0 + h) =
+                (uint32_t)barg[h] | ((uint32_t)barg[h + 1] << 8) | ((uint32_t)barg[h + 2] << 16) | ((uint32_t)barg[h + 3] << 24);
+        }
     }
     if (stats) {
-        int chans[4] = {c0, c0 + 1, c0 + 2, c0 + 3};
-        fs_stats_commit<4>(red, s1, s2, chans, Q, CP, stats);
-        if (blockIdx.x == 0 && r == 0) {
-            __syncthreads();
+        double d1[V], d2[V];
+        int chans[V];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) stats[2 * CP + c0 + i] = (double)pivot[i];
+        for (int i = 0; i < V; ++i) { d1[i] = (double)t1[i]; d2[i] = (double)t2[i]; chans[i] = c0 + i; }
+        fs_stats_commit<V>(red, d1, d2, chans, Q, CP, stats);
+        if (blockIdx.x == 0 && r == 0) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) stats[2 * CP + c0 + i] = (double)pivot[i];
         }
     }
 }
@@ -604,31 +622,52 @@ __global__ void __launch_bounds__(256)
 edge_reduce_bwd_kernel(const ZT* __restrict__ z, const float* __restrict__ d, const uint8_t* __restrict__ arg,
                        long long P, int k, const float* __restrict__ coef, const double* __restrict__ dgb, double count,
                        int train_stats, DT* __restrict__ dz) {
-    constexpr int Q = CP / 4;
+    constexpr int V = FsRow<ZT>::VEC;
+    constexpr int Q = CP / V;
     constexpr int ROWS = 256 / Q;
     const int l = threadIdx.x % Q;
     const int r = threadIdx.x / Q;
-    const int c0 = l * 4;
-    float mu[4], inv[4], sc[4], mb[4], mg[4];
+    const int c0 = l * V;
+    float mu[V], sc[V], mb[V], mg[V];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        mu[i] = __ldg(coef + c0 + i); inv[i] = __ldg(coef + CP + c0 + i); sc[i] = __ldg(coef + 2 * CP + c0 + i);
+    for (int i = 0; i < V; ++i) {
+        mu[i] = __ldg(coef + c0 + i); sc[i] = __ldg(coef + 2 * CP + c0 + i);
         mb[i] = train_stats ? (float)(dgb[c0 + i] / count) : 0.f;
-        mg[i] = train_stats ? (float)(dgb[CP + c0 + i] / count) * inv[i] : 0.f;
+        mg[i] = train_stats ? (float)(dgb[CP + c0 + i] / count) * __ldg(coef + CP + c0 + i) : 0.f;
     }
     for (long long pt = (long long)blockIdx.x * ROWS + r; pt < P; pt += (long long)gridDim.x * ROWS) {
-        float dv[4];
-        load4(d + pt * CP + c0, dv);
-        const uint32_t pk = __ldg(reinterpret_cast<const uint32_t*>(arg + pt * CP + c0));
-        for (int t = 0; t < k; ++t) {
-            float zv[4], o[4];
-            if (train_stats) load4(z + (pt * k + t) * CP + c0, zv);
+        float dv[V];
+        int ar[V];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float routed = (int)((pk >> (8 * i)) & 0xff) == t ? dv[i] : 0.f;
-                o[i] = train_stats ? sc[i] * (routed - mb[i] - mg[i] * (zv[i] - mu[i])) : sc[i] * routed;
+        for (int h = 0; h < V; h += 4) {
+            load4(d + pt * CP + c0 + h, dv + h);
+            const uint32_t pk = __ldg(reinterpret_cast<const uint32_t*>(arg + pt * CP + c0 + h));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ar[h + i] = (int)((pk >> (8 * i)) & 0xff);
+        }
+        for (int t0 = 0; t0 < k; t0 += 2) {
+            float zv[2][V];
+            if (train_stats) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) FsRow<ZT>::load(z + (pt * k + (t0 + u < k ? t0 + u : k - 1)) * CP + c0, zv[u]);
             }
-            store4(dz + (pt * k + t) * CP + c0, o);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (t0 + u < k) {
+                    float o[V];
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        const float routed = ar[i] == t0 + u ? dv[i] : 0.f;
+                        o[i] = train_stats ? sc[i] * (routed - mb[i] - mg[i] * (zv[u][i] - mu[i])) : sc[i] * routed;
+                    }
+                    DT* op = dz + (pt * k + t0 + u) * CP + c0;
+                    if (sizeof(DT) == 2 && V == 8) FsRow<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(op), o);
+                    else {
+#pragma unroll
+                        for (int h = 0; h < V; h += 4) store4(op + h, o + h);
+                    }
+                }
+            }
         }
     }
 }
@@ -900,7 +939,7 @@ extern "C" int fs_edge_reduce(int device, fs_stream_t stream_, const void* z, in
     cudaStream_t stream = (cudaStream_t)stream_;
 #define GO(CP)                                                                                                   \
     if (z_dtype == FS_BF16)                                                                                      \
-        edge_reduce_kernel<__nv_bfloat16, CP><<<ec_grid(P, 256 / (CP / 4)), 256, 0, stream>>>((const __nv_bfloat16*)z, P, k, gamma, sel, arg, sy, stats); \
+        edge_reduce_kernel<__nv_bfloat16, CP><<<ec_grid(P, 256 / (CP / 8)), 256, 0, stream>>>((const __nv_bfloat16*)z, P, k, gamma, sel, arg, sy, stats); \
     else                                                                                                         \
         edge_reduce_kernel<float, CP><<<ec_grid(P, 256 / (CP / 4)), 256, 0, stream>>>((const float*)z, P, k, gamma, sel, arg, sy, stats);
     EC_DISPATCH_CP(Cp, GO)
@@ -918,7 +957,7 @@ extern "C" int fs_edge_reduce_bwd(int device, fs_stream_t stream_, const void* z
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
 #define GO2(CP, ZT, DT)                                                                                   \
-    edge_reduce_bwd_kernel<ZT, DT, CP><<<ec_grid(P, 256 / (CP / 4)), 256, 0, stream>>>(                   \
+    edge_reduce_bwd_kernel<ZT, DT, CP><<<ec_grid(P, 256 / (CP / FsRow<ZT>::VEC)), 256, 0, stream>>>(                   \
         (const ZT*)z, d, arg, P, k, coef, dgb, count, train_stats, (DT*)dz)
 #define GO(CP)                                                                       \
     if (z_dtype == FS_BF16 && dz_dtype == FS_BF16) GO2(CP, __nv_bfloat16, __nv_bfloat16); \

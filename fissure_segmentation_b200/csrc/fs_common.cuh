@@ -123,8 +123,9 @@ __host__ __device__ inline long long fs_stats_doubles(int C) { return 3ll * C + 
 // Threads whose (threadIdx.x % period) agree own the same NCH channels chan[0..NCH).
 // buf: shared double[2 * NCH * blockDim.x]. Every thread of the block must call this exactly once per kernel.
 template <int NCH>
-__device__ __forceinline__ void fs_stats_commit(double* buf, const double* s1, const double* s2, const int* chan,
-                                                int period, int C, double* gstats) {
+__device__ __forceinline__ void fs_stats_commit_impl(double* buf, const double* s1, const double* s2, const int* chan,
+                                                     int period, int C, double* gstats, unsigned block_linear,
+                                                     unsigned num_blocks) {
     const int T = blockDim.x, t = threadIdx.x;
     __shared__ bool fs_last_block;
 #pragma unroll
@@ -134,7 +135,7 @@ __device__ __forceinline__ void fs_stats_commit(double* buf, const double* s1, c
     }
     __syncthreads();
     const int slots = fs_stat_slots(C);
-    double* slot = gstats + 3 * C + (blockIdx.x % slots) * 2 * C;
+    double* slot = gstats + 3 * C + (block_linear % slots) * 2 * C;
     if (t < period) {
 #pragma unroll
         for (int e = 0; e < NCH; ++e) {
@@ -147,7 +148,7 @@ __device__ __forceinline__ void fs_stats_commit(double* buf, const double* s1, c
     __threadfence();
     __syncthreads();
     unsigned* ticket = reinterpret_cast<unsigned*>(gstats + 3 * C + slots * 2 * C);
-    if (t == 0) fs_last_block = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (t == 0) fs_last_block = atomicAdd(ticket, 1u) == num_blocks - 1;
     __syncthreads();
     if (fs_last_block) {
         __threadfence();
@@ -157,4 +158,16 @@ __device__ __forceinline__ void fs_stats_commit(double* buf, const double* s1, c
             gstats[c] = a;
         }
     }
+}
+
+template <int NCH>
+__device__ __forceinline__ void fs_stats_commit(double* buf, const double* s1, const double* s2, const int* chan,
+                                                int period, int C, double* gstats) {
+    fs_stats_commit_impl<NCH>(buf, s1, s2, chan, period, C, gstats, blockIdx.x, gridDim.x);
+}
+template <int NCH>
+__device__ __forceinline__ void fs_stats_commit_2d(double* buf, const double* s1, const double* s2, const int* chan,
+                                                   int period, int C, double* gstats) {
+    fs_stats_commit_impl<NCH>(buf, s1, s2, chan, period, C, gstats, blockIdx.y * gridDim.x + blockIdx.x,
+                              gridDim.x * gridDim.y);
 }

@@ -393,7 +393,8 @@ class _PoolBnActFn(torch.autograd.Function):
         sel = torch.empty(B, C, dtype=torch.float32, device=dev)
         arg = torch.empty(B, C, dtype=torch.int32, device=dev)
         stats = _stats_buffer(C, dev) if training else None
-        _lib.call("fs_pool_reduce", x, x, _lib.dtype_code(x), x.stride(0), B, N, C, gamma32, sel, arg, stats)
+        packed = torch.zeros(B * C, dtype=torch.int64, device=dev)
+        _lib.call("fs_pool_reduce", x, x, _lib.dtype_code(x), x.stride(0), B, N, C, gamma32, sel, arg, stats, packed)
         coef = _bn_coef(x, stats, B * N, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
         out = torch.empty(B, C, dtype=x.dtype, device=dev)
         _lib.call("fs_bn_act_apply", x, sel, 0, C, B, C, None, 1, coef, float(slope), out, _lib.dtype_code(out), C)

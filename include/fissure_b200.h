@@ -290,7 +290,8 @@ int fs_bn_act_bwd(int device, fs_stream_t stream, const void* g, int g_dtype, in
  *   fs_pool_bwd     dX[r,c] = scale*([r==arg[b,c]]*g[b,c]*LeakyReLU'(z_sel) - dbeta/M - xhat*dgamma/M)
  */
 int fs_pool_reduce(int device, fs_stream_t stream, const void* x, int dtype, int ld, int B, int N, int C,
-                   const float* gamma, float* sel, int32_t* arg, double* stats);
+                   const float* gamma, float* sel, int32_t* arg, double* stats,
+                   unsigned long long* packed_ws /* [B*C], zero-filled */);
 int fs_pool_bwd(int device, fs_stream_t stream, const void* x, int dtype, int ld, int B, int N, int C,
                 const float* g, const float* sel, const int32_t* arg, const float* coef, float slope,
                 const double* dgb, double count, int train_stats, void* dx, int dx_dtype, int ld_dx);
