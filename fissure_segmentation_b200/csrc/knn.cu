@@ -116,16 +116,12 @@ knn3d_regs_kernel(const float* __restrict__ coords, long long batch_stride, long
                   int32_t* __restrict__ idx, float* __restrict__ dist2) {
     constexpr int CAP = 32 * CPL * 2;                         // survivor queue entries per warp
     extern __shared__ float smem[];
-    const int chunk = NPL * 32;
-    float* sx = smem;
-    float* sy = sx + chunk;
-    float* sz = sy + chunk;
-    float* sn = sz + chunk;
-    float* qd_all = sn + chunk;                               // [warps][64] warp-select queue
+    constexpr int chunk = NPL * 32;
+    float4* sp = reinterpret_cast<float4*>(smem);             // staged cloud: (x, y, z, |p|^2) per point, one LDS.128
+    float* qd_all = smem + 4 * chunk;                         // [warps][64] warp-select queue
     int* qi_all = reinterpret_cast<int*>(qd_all + KNN3R_WARPS * 64);
     float* hd_all = reinterpret_cast<float*>(qi_all + KNN3R_WARPS * 64);   // [warps][CAP] survivors
     int* hi_all = reinterpret_cast<int*>(hd_all + KNN3R_WARPS * CAP);
-    int* hn_all = hi_all + KNN3R_WARPS * CAP;                 // [warps] survivor counters
 
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5;
@@ -134,12 +130,13 @@ knn3d_regs_kernel(const float* __restrict__ coords, long long batch_stride, long
     const int kk = k + (self_loop ? 0 : 1);
 
     for (int j = threadIdx.x; j < chunk; j += KNN3R_THREADS) {
-        float x = 0.f, y = 0.f, z = 0.f;
+        float4 p = make_float4(0.f, 0.f, 0.f, INFINITY);      // padding beyond the cloud: distance +inf, no per-candidate bound check
         if (j < N) {
             const long long o = (long long)j * point_stride;
-            x = __ldg(cb + o); y = __ldg(cb + chan_stride + o); z = __ldg(cb + 2 * chan_stride + o);
+            p.x = __ldg(cb + o); p.y = __ldg(cb + chan_stride + o); p.z = __ldg(cb + 2 * chan_stride + o);
+            p.w = sqnorm3(p.x, p.y, p.z);
         }
-        sx[j] = x; sy[j] = y; sz[j] = z; sn[j] = sqnorm3(x, y, z);
+        sp[j] = p;
     }
     __syncthreads();
 
@@ -150,28 +147,37 @@ knn3d_regs_kernel(const float* __restrict__ coords, long long batch_stride, long
     for (int r = 0; r < KNN3R_QPW; ++r) {
         const int q = blockIdx.x * KNN3R_TILE_Q + r * KNN3R_WARPS + warp;
         if (q >= N) break;                                    // warp-uniform
-        const float qx = sx[q], qy = sy[q], qz = sz[q], qq = sn[q];
+        const float4 qp = sp[q];
+        const float qx = qp.x, qy = qp.y, qz = qp.z, qq = qp.w;
+        const int self_i = diag_zero ? (q >> 5) : -1, self_lane = q & 31;
         float dist[NPL];
         float cm[CPL];
 #pragma unroll
         for (int c = 0; c < CPL; ++c) cm[c] = INFINITY;
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
-            const int j = i * 32 + lane;
-            const float dot = fmaf(qz, sz[j], fmaf(qy, sy[j], __fmul_rn(qx, sx[j])));
-            float d = diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * dot), sn[j]) : __fadd_rn(__fsub_rn(sn[j], 2.0f * dot), qq);
-            if (diag_zero && j == q) d = 0.f;
-            if (j >= N) d = INFINITY;
+            const float4 p = sp[i * 32 + lane];
+            const float dot = fmaf(qz, p.z, fmaf(qy, p.y, __fmul_rn(qx, p.x)));
+            float d = diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * dot), p.w) : __fadd_rn(__fsub_rn(p.w, 2.0f * dot), qq);
+            if (i == self_i && lane == self_lane) d = 0.f;    // general_utils.py:52
             dist[i] = d;
             cm[i % CPL] = fminf(cm[i % CPL], d);
         }
-        // tau = kk-th smallest class minimum
-        sel.init(qd_all + warp * 64, qi_all + warp * 64, kk);
+        // tau = kk-th smallest of the 32*CPL class minima
+        float tau;
+        if (CPL == 1) {
+            float td = cm[0];
+            int ti = lane;
+            fs_warp_bitonic_sort(td, ti, lane);
+            tau = __shfl_sync(FS_FULL_MASK, td, kk - 1);
+        } else {
+            sel.init(qd_all + warp * 64, qi_all + warp * 64, kk);
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) sel.offer(cm[c], c * 32 + lane, true);
-        sel.finish();
-        float tau; int tj;
-        sel.get(kk - 1, tau, tj);
+            for (int c = 0; c < CPL; ++c) sel.offer(cm[c], c * 32 + lane, true);
+            sel.finish();
+            int tj;
+            sel.get(kk - 1, tau, tj);
+        }
         // collect survivors without atomics: per-lane hit count, exclusive scan over the lanes, private writes
         int mine = 0;
 #pragma unroll
@@ -191,6 +197,20 @@ knn3d_regs_kernel(const float* __restrict__ coords, long long batch_stride, long
             }
         }
         __syncwarp();
+        const long long row = ((long long)b * N + q) * k;
+        if (n <= 32 && n >= kk && tau < INFINITY) {
+            // common case: one 32-wide bitonic sort of the survivors gives the answer
+            float sd = lane < n ? hd[lane] : INFINITY;
+            int sj = lane < n ? hi[lane] : FS_IDX_PAD;
+            fs_warp_bitonic_sort(sd, sj, lane);
+            const int skip = self_loop ? 0 : 1;
+            if (lane >= skip && lane < kk) {
+                idx[row + lane - skip] = sj;
+                if (dist2) dist2[row + lane - skip] = sd;
+            }
+            __syncwarp();
+            continue;
+        }
         sel.init(qd_all + warp * 64, qi_all + warp * 64, kk);
         if (n <= CAP && tau < INFINITY) {
             for (int base = 0; base < n; base += 32) {
@@ -204,14 +224,14 @@ knn3d_regs_kernel(const float* __restrict__ coords, long long batch_stride, long
 #pragma unroll 1
             for (int i = 0; i < NPL; ++i) {
                 const int j = i * 32 + lane;
-                const float dot = fmaf(qz, sz[j], fmaf(qy, sy[j], __fmul_rn(qx, sx[j])));
-                float d = diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * dot), sn[j]) : __fadd_rn(__fsub_rn(sn[j], 2.0f * dot), qq);
+                const float4 p = sp[j];
+                const float dot = fmaf(qz, p.z, fmaf(qy, p.y, __fmul_rn(qx, p.x)));
+                float d = diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * dot), p.w) : __fadd_rn(__fsub_rn(p.w, 2.0f * dot), qq);
                 if (diag_zero && j == q) d = 0.f;
                 sel.offer(d, j, j < N);
             }
         }
         sel.finish();
-        const long long row = ((long long)b * N + q) * k;
         sel.store(self_loop ? 0 : 1, idx + row, dist2 ? dist2 + row : nullptr, 0, 0, INFINITY);
         __syncwarp();
     }
@@ -398,13 +418,15 @@ extern "C" int fs_knn3d(int device, fs_stream_t stream_, const float* coords, lo
 #define LAUNCH3R(NPL, CPL, KPL)                                                                                  \
     do {                                                                                                         \
         const size_t rs = (size_t)(NPL) * 32 * 4 * sizeof(float) + KNN3R_WARPS * 64 * 8 +                        \
-                          (size_t)KNN3R_WARPS * (32 * (CPL) * 2) * 8 + KNN3R_WARPS * sizeof(int);                \
+                          (size_t)KNN3R_WARPS * (32 * (CPL) * 2) * 8;                                            \
         int e = set_smem(knn3d_regs_kernel<NPL, CPL, KPL>, rs);                                                  \
         if (e) return e;                                                                                         \
         knn3d_regs_kernel<NPL, CPL, KPL><<<rgrid, KNN3R_THREADS, rs, stream>>>(                                  \
             coords, batch_stride, chan_stride, point_stride, N, k, self_loop, diag_zero, idx, dist2);            \
     } while (0)
-        if (kk <= 32) {
+        if (kk <= 22) {          // 32 class minima: tau near rank 32 ln(32 / (32 - kk)) <= 37
+            if (N <= 1024) LAUNCH3R(32, 1, 1); else LAUNCH3R(64, 1, 1);
+        } else if (kk <= 32) {
             if (N <= 1024) LAUNCH3R(32, 2, 1); else LAUNCH3R(64, 2, 1);
         } else {
             if (N <= 1024) LAUNCH3R(32, 4, 2); else LAUNCH3R(64, 4, 2);
