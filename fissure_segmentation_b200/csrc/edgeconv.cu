@@ -6,6 +6,9 @@
 // BatchNorm(affine) followed by LeakyReLU is monotone per channel, so max over k commutes with it:
 // only max_j a_j (gamma >= 0) or min_j a_j (gamma < 0) is needed, plus the batch sums of y = a_j+b_i.
 #include "fs_common.cuh"
+#include "edgeconv_smem.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -697,6 +700,13 @@ int ec_grid(long long rows, int rows_per_block) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// FS_GATHER=global forces the global-memory gather kernel (A/B measurements); default: shared-memory-resident
+// slices whenever the shape fits (edgeconv_smem.cu).
+static bool use_smem_gather() {
+    const char* e = getenv("FS_GATHER");     // read per call: tests and benchmarks toggle it at run time
+    return !(e && strcmp(e, "global") == 0);
+}
+
 #define EC_DISPATCH_CP(Cp, MACRO) \
     switch (Cp) {                 \
         case 64: MACRO(64); break; \
@@ -717,6 +727,11 @@ extern "C" int fs_edgeconv_gather(int device, fs_stream_t stream_, const void* t
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long P = (long long)B * N;
+    if (dtype == FS_F32 && use_smem_gather() && aligned16(sel) && (!sy || aligned16(sy))) {
+        const int rc = fs_gather_smem_train(stream, (const float*)table, ld, idx, B, N, k, Cp, gamma, rev_ptr, sel, arg,
+                                            sy, stats);
+        if (rc != FS_SMEM_GATHER_UNSUPPORTED) return rc;
+    }
 #define GO(CP)                                                                                                  \
     if (dtype == FS_BF16) {                                                                                     \
         using M = EcMap<__nv_bfloat16, CP>;                                                                     \
@@ -746,6 +761,11 @@ extern "C" int fs_edgeconv_fused_eval(int device, fs_stream_t stream_, const voi
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long P = (long long)B * N;
+    if (dtype == FS_F32 && use_smem_gather()) {
+        const int rc = fs_gather_smem_eval(stream, (const float*)table, ld, idx, B, N, k, Cp, coef, out,
+                                           out_dtype == FS_BF16, ld_out, arg);
+        if (rc != FS_SMEM_GATHER_UNSUPPORTED) return rc;
+    }
 #define GO2(CP, TT, OT)                                                                                         \
     edgeconv_gather_kernel<TT, CP, 1, OT><<<gather_grid(P, EC_WARPS * EcMap<TT, CP>::PPW), EC_THREADS, 0, stream>>>( \
         (const TT*)table, ld, idx, P, N, k, coef, nullptr, nullptr, arg, nullptr, nullptr, (OT*)out, ld_out)

@@ -86,6 +86,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+// One elected lane of a converged warp (ptxas then knows a single thread is active and issues the tcgen05 /
+// TMA instructions straight from uniform registers instead of a per-lane waterfall loop).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -363,7 +374,7 @@ knn_tc_select_kernel(const __nv_bfloat16* __restrict__ a_rows, long long P, cons
             mbar_wait(smem_u32(b_full + s), (it / TC_STAGES) & 1);            // operands landed
             mbar_wait(smem_u32(acc_empty + a), ((it / TC_ACC) & 1) ^ 1);      // accumulator buffer drained by the epilogue
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
+            if (elect_one_sync()) {
                 const uint64_t db_s = db0 + (uint64_t)((s * TC_BTILE_BYTES) >> 4);
                 const uint32_t acc_a = tmem_base + TC_TMEM_ACC0 + a * TC_QT * TC_NB;
 #pragma unroll
