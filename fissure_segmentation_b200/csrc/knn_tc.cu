@@ -37,18 +37,19 @@ constexpr int TC_ABOX_BYTES = TC_M * 128;
 constexpr int TC_ATILE_BYTES = TC_BOXES * TC_ABOX_BYTES;     // 64 KB
 constexpr int TC_BBOX_BYTES = TC_NB * 128;
 constexpr int TC_BTILE_BYTES = TC_BOXES * TC_BBOX_BYTES;     // 32 KB
-constexpr int TC_STAGES = 6;         // smem stages of the candidate (B) tiles (32 KB each)
+constexpr int TC_STAGES = 5;         // smem stages of the candidate (B) tiles (32 KB each)
 constexpr int TC_ACC = 2;            // TMEM accumulator buffers (each holds TC_QT tiles of TC_NB columns)
 constexpr int TC_KSTEPS = 13;        // K = 16 steps: 12 data (hi*hi, lo*hi, hi*lo) + 1 extras
 constexpr int TC_A_COLS = TC_KSTEPS * 8;   // TMEM columns of one query tile's A operand (2 bf16 per 32-bit column)
-constexpr int TC_EPI_WARPS = 4 * TC_QT;   // one epilogue warpgroup per query tile (TMEM lane = query row)
+constexpr int TC_HALVES = TC_NB / 32;     // 32-column halves of a candidate tile, one epilogue warp each
+constexpr int TC_EPI_WARPS = 4 * TC_QT * TC_HALVES;   // warp w: TMEM lane quarter w & 3, query tile (w >> 2) & 1, column half w >> 3
 constexpr int TC_WARP_TMA = TC_EPI_WARPS;
 constexpr int TC_WARP_MMA = TC_EPI_WARPS + 1;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr int TC_STAGE_BYTES = 32 * 32 * 4;  // per-warp staging of one 32 x 32 score block (sweep 2)
-constexpr int TC_CAP = 128;        // survivor slots per query (observed: mean 26-33, max 68)
-constexpr int TC_NCLS = 32;        // interleaved column classes of sweep 1
-constexpr int TC_MAX_KK = 24;      // kk-th smallest of 32 class minima stays near rank 1.6 kk up to here
+constexpr int TC_CAP = 128;        // survivor slots per query (observed: mean 26-33, max 68), TC_CAP / 2 per column half
+constexpr int TC_NCLS = 32;        // interleaved column classes of sweep 1, per 32-column half (64 per row)
+constexpr int TC_MAX_KK = 32;      // the merged list holds the 32 smallest of the 64 class minima
 constexpr int TC_TMEM_ACC0 = 256;     // accumulators at columns [256, 512), A operands at [0, 2*104)
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_BTILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * TC_STAGE_BYTES;
@@ -70,9 +71,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug traps instead of hanging the GPU.
+// Spin on the phase parity. FS_TC_BOUNDED_WAIT (debug builds) traps after ~2 s instead of hanging on a protocol bug;
+// the release loop carries no clock reads (they cost six extra issue slots per spin in the hot epilogue warps).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef FS_TC_BOUNDED_WAIT
     const long long t0 = clock64();
+#endif
     while (true) {
         uint32_t done;
         asm volatile(
@@ -83,7 +87,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return;
+#ifdef FS_TC_BOUNDED_WAIT
         if (clock64() - t0 > 4000000000LL) __trap();
+#endif
     }
 }
 // One elected lane of a converged warp (ptxas then knows a single thread is active and issues the tcgen05 /
@@ -391,21 +397,25 @@ knn_tc_select_kernel(const __nv_bfloat16* __restrict__ a_rows, long long P, cons
             __syncwarp();
         }
     } else {
-        // ===================== epilogue: warpgroup u owns query tile u, TMEM lane = query row =====================
-        const int u = warp >> 2;                       // query tile of this warpgroup
+        // ===================== epilogue: TMEM lane = query row; two warps share a row, one per 32-column half ======
+        const int u = (warp >> 2) & (TC_QT - 1);       // query tile
         const int w4 = warp & 3;                       // TMEM lane quarter this warp may access
+        const int cb = warp >> 3;                      // column half of every candidate tile
         const int qrow = q_row0 + u * TC_M + w4 * 32 + lane;
         const bool row_ok = qrow < N;
         const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
         {
-            // A operand: this thread's query row -> TMEM (columns u*104 .. +104); rows past the table are zero
+            // A operand: this thread's query row -> TMEM (columns u*104 .. +104), the K steps split between the two
+            // warps of the row; rows past the table are zero
             const long long grow = cloud0 + qrow;
             const uint4* src = reinterpret_cast<const uint4*>(a_rows + (grow < P ? grow : 0) * TC_KROW);
 #pragma unroll
             for (int st = 0; st < TC_KSTEPS; ++st) {
-                uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-                if (grow < P) { lo = __ldg(src + 2 * st); hi = __ldg(src + 2 * st + 1); }
-                tmem_st8(tmem_base + lane_base + (uint32_t)(u * TC_A_COLS + st * 8), lo, hi);
+                if ((st < (TC_KSTEPS + 1) / 2) == (cb == 0)) {          // warp-uniform
+                    uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+                    if (grow < P) { lo = __ldg(src + 2 * st); hi = __ldg(src + 2 * st + 1); }
+                    tmem_st8(tmem_base + lane_base + (uint32_t)(u * TC_A_COLS + st * 8), lo, hi);
+                }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -418,76 +428,94 @@ knn_tc_select_kernel(const __nv_bfloat16* __restrict__ a_rows, long long P, cons
         for (int e = 0; e < TC_NCLS; ++e) gm[e] = INFINITY;
         float tau = INFINITY;
         int cnt = 0;
-        const long long out_base = (cloud0 + (row_ok ? qrow : 0)) * TC_CAP;
+        const long long out_base = (cloud0 + (row_ok ? qrow : 0)) * TC_CAP + cb * (TC_CAP / TC_HALVES);
         for (int it = 0; it < 2 * T; ++it) {
             const int a = it % TC_ACC;
             const uint32_t ph = (it / TC_ACC) & 1;
-            const int j0 = (it % T) * TC_NB;
+            const int jb = (it % T) * TC_NB + cb * 32;
             if (it == T) {
-                // between the sweeps: tau = kk-th smallest class minimum (+ 2 err); bitonic network in registers
+                // between the sweeps: the two column halves of a row hold 32 class minima each over DISJOINT candidate
+                // sets = 64 classes. Each thread sorts its own 32, the pair exchanges them through the staging blocks
+                // (named barrier per warp pair); min(own[i], other[31-i]) is the (bitonic) lower half of the union,
+                // one bitonic merge sorts it. tau = kk-th smallest of the 64 class minima (+ 2 err): on average
+                // 24 survivors per row for kk = 20 instead of 30.6 with 32 classes.
+                const int pair_bar = 1 + (warp & 7);
                 bitonic_sort32(gm);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4*>(stage + ((c ^ (lane & 7)) << 2)) = make_float4(gm[4 * c], gm[4 * c + 1], gm[4 * c + 2], gm[4 * c + 3]);
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                const float* other = stage_all + (warp ^ 8) * (TC_STAGE_BYTES / 4) + lane * 32;
+                float og[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 o = *reinterpret_cast<const float4*>(other + ((c ^ (lane & 7)) << 2));
+                    og[4 * c] = o.x; og[4 * c + 1] = o.y; og[4 * c + 2] = o.z; og[4 * c + 3] = o.w;
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // staging blocks are reused by sweep 2
+#pragma unroll
+                for (int i = 0; i < 32; ++i) gm[i] = fminf(gm[i], og[31 - i]);
+                bitonic_layer32<32, 16>(gm); bitonic_layer32<32, 8>(gm); bitonic_layer32<32, 4>(gm);
+                bitonic_layer32<32, 2>(gm); bitonic_layer32<32, 1>(gm);
                 float t = -INFINITY;   // sorted ascending: kk-th smallest = max of the first kk (no indexed register access)
 #pragma unroll
                 for (int i = 0; i < TC_NCLS; ++i) t = fmaxf(t, i < kk ? gm[i] : -INFINITY);
                 const float cmax = __int_as_float(__ldg(norm_max_bits + 2 * b)), rmax = __int_as_float(__ldg(norm_max_bits + 2 * b + 1));
                 const int q = row_ok ? qrow : N - 1;
                 tau = t + 2.f * tc_row_err(__ldg(cnorm + cloud0 + q), cmax, __ldg(sqnorm + cloud0 + q), rmax);
+                // strictly above tau: the hit test below is the sign bit of (score - tau)
+                tau = tau + fmaxf(fabsf(tau) * 2.4e-7f, 1e-37f);
             }
             mbar_wait(smem_u32(acc_full + a), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // Both 32-column blocks of this thread's row are pulled into registers and the accumulator buffer is
-            // handed back to the MMA warp BEFORE the scores are processed.
-            float v[TC_NB / 32][32];
-#pragma unroll
-            for (int cb = 0; cb < TC_NB / 32; ++cb)
-                tmem_ld32_nowait(tmem_base + lane_base + (uint32_t)(TC_TMEM_ACC0 + (a * TC_QT + u) * TC_NB + cb * 32), v[cb]);
+            // This thread's 32 scores are pulled into registers and the accumulator buffer is handed back to the MMA
+            // warp BEFORE the scores are processed.
+            float v[32];
+            tmem_ld32_nowait(tmem_base + lane_base + (uint32_t)(TC_TMEM_ACC0 + (a * TC_QT + u) * TC_NB + cb * 32), v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(acc_empty + a));
+            if (jb + 32 > N) {         // last tile: columns beyond the cloud are padding / the next cloud
 #pragma unroll
-            for (int cb = 0; cb < TC_NB / 32; ++cb) {
-                const int jb = j0 + cb * 32;
-                if (jb + 32 > N) {         // last tile: columns beyond the cloud are padding / the next cloud
+                for (int e = 0; e < 32; ++e) v[e] = (jb + e < N) ? v[e] : INFINITY;
+            }
+            if (diag_zero && jb == q_row0 + u * TC_M + w4 * 32) {      // warp-uniform: this block holds the warp's diagonal
+                // the reference forces d(i,i) = 0 (general_utils.py:52): the query itself always survives
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[cb][e] = (jb + e < N) ? v[cb][e] : INFINITY;
-                }
-                if (diag_zero && __any_sync(FS_FULL_MASK, qrow >= jb && qrow < jb + 32)) {
-                    // the reference forces d(i,i) = 0 (general_utils.py:52): the query itself always survives
+                for (int e = 0; e < 32; ++e) v[e] = (jb + e == qrow) ? -FLT_MAX : v[e];
+            }
+            if (it < T) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[cb][e] = (jb + e == qrow) ? -FLT_MAX : v[cb][e];
-                }
-                if (it < T) {
+                for (int e = 0; e < 32; ++e) gm[e] = fminf(gm[e], v[e]);
+            } else {
+                // sweep 2: hit mask from sign bits (one FADD + one funnel shift per score), scores staged in shared
+                // memory (16-byte chunks XOR-swizzled by lane so the 128-bit stores are conflict-free), then each
+                // lane walks its own few hits
+                unsigned hits = 0;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) gm[e] = fminf(gm[e], v[cb][e]);
-                } else {
-                    // sweep 2: branch-free hit mask, scores staged in shared memory (16-byte chunks XOR-swizzled by
-                    // lane so the 128-bit stores are conflict-free), then each lane walks its own few hits
-                    unsigned hits = 0;
+                for (int e = 31; e >= 0; --e) hits = __funnelshift_l(__float_as_uint(v[e] - tau), hits, 1);
+                if (!row_ok) hits = 0;
+                if (__any_sync(FS_FULL_MASK, hits != 0)) {
+                    __syncwarp();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) hits |= (v[cb][e] <= tau) ? (1u << e) : 0u;
-                    if (!row_ok) hits = 0;
-                    if (__any_sync(FS_FULL_MASK, hits != 0)) {
-                        __syncwarp();
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            *reinterpret_cast<float4*>(stage + ((c ^ (lane & 7)) << 2)) =
-                                make_float4(v[cb][4 * c], v[cb][4 * c + 1], v[cb][4 * c + 2], v[cb][4 * c + 3]);
-                        while (hits) {
-                            const int e = __ffs(hits) - 1;
-                            hits &= hits - 1;
-                            const float dv = stage[(((e >> 2) ^ (lane & 7)) << 2) + (e & 3)];
-                            if (cnt < TC_CAP) {
-                                cand_j[out_base + cnt] = jb + e;
-                                cand_d[out_base + cnt] = dv;
-                            }
-                            ++cnt;
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<float4*>(stage + ((c ^ (lane & 7)) << 2)) =
+                            make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    while (hits) {
+                        const int e = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const float dv = stage[(((e >> 2) ^ (lane & 7)) << 2) + (e & 3)];
+                        if (cnt < TC_CAP / TC_HALVES) {
+                            cand_j[out_base + cnt] = jb + e;
+                            cand_d[out_base + cnt] = dv;
                         }
+                        ++cnt;
                     }
                 }
             }
         }
-        if (row_ok) cand_n[cloud0 + qrow] = cnt;
+        if (row_ok) cand_n[(cloud0 + qrow) * TC_HALVES + cb] = cnt;
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -503,18 +531,28 @@ knn_tc_select_kernel(const __nv_bfloat16* __restrict__ a_rows, long long P, cons
 // H = entries per lane: 1 when the row has at most 32 survivors (one 32-wide bitonic sort), else 2.
 template <int H>
 __device__ __forceinline__ void tc_finalize_row(const float* __restrict__ x, int ldx, long long cloud0, int q, long long row,
-                                                int k, int kk, int skip, int diag_zero, int n,
+                                                int k, int kk, int skip, int diag_zero, int n, int n0,
                                                 const int32_t* __restrict__ cand_j, const float* __restrict__ cand_d,
                                                 const float* __restrict__ sqnorm, float err, float qq,
                                                 float* qd, int* qi, float* xq, int32_t* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     float sd[H];
     int sj[H];
-    if (H == 1) {
-        const bool valid = lane < n;
-        sd[0] = valid ? __ldg(cand_d + row * TC_CAP + lane) : INFINITY;
-        sj[0] = valid ? __ldg(cand_j + row * TC_CAP + lane) : FS_IDX_PAD;
-        fs_warp_bitonic_sort(sd[0], sj[0], lane);
+    // survivors of the two column halves sit in [0, n0) and [TC_CAP/2, TC_CAP/2 + n - n0)
+    auto phys = [&](int slot) { return slot < n0 ? slot : TC_CAP / TC_HALVES + slot - n0; };
+    if (H <= 2) {
+        // one or two survivors per lane: bitonic network on packed (distance, index) keys
+        unsigned long long key[H <= 2 ? H : 1];
+#pragma unroll
+        for (int h = 0; h < (H <= 2 ? H : 1); ++h) {
+            const int slot = h * 32 + lane;
+            const bool valid = slot < n;
+            key[h] = fs_pack_key(valid ? __ldg(cand_d + row * TC_CAP + phys(slot)) : INFINITY,
+                                 valid ? __ldg(cand_j + row * TC_CAP + phys(slot)) : FS_IDX_PAD);
+        }
+        fs_warp_bitonic_sort_keys<(H <= 2 ? H : 1)>(key, lane);
+#pragma unroll
+        for (int h = 0; h < (H <= 2 ? H : 1); ++h) fs_unpack_key(key[h], sd[h], sj[h]);
     } else {
         FsWarpSelect<H> sel;
         sel.init(qd, qi, 32 * H);
@@ -522,7 +560,7 @@ __device__ __forceinline__ void tc_finalize_row(const float* __restrict__ x, int
         for (int h = 0; h < H; ++h) {
             const int slot = h * 32 + lane;
             const bool valid = slot < n;
-            sel.offer(valid ? __ldg(cand_d + row * TC_CAP + slot) : INFINITY, valid ? __ldg(cand_j + row * TC_CAP + slot) : FS_IDX_PAD, valid);
+            sel.offer(valid ? __ldg(cand_d + row * TC_CAP + phys(slot)) : INFINITY, valid ? __ldg(cand_j + row * TC_CAP + phys(slot)) : FS_IDX_PAD, valid);
         }
         sel.finish();
 #pragma unroll
@@ -584,16 +622,15 @@ __device__ __forceinline__ void tc_finalize_row(const float* __restrict__ x, int
     for (int h = 0; h < H; ++h) rank[h] = 0;
 #pragma unroll
     for (int sh = 0; sh < H; ++sh) {
-        if (!__any_sync(FS_FULL_MASK, amb[sh])) continue;
-        for (int sl = 0; sl < 32; ++sl) {
+        unsigned todo = __ballot_sync(FS_FULL_MASK, amb[sh]);      // only the ambiguous lanes are broadcast
+        while (todo) {
+            const int sl = __ffs(todo) - 1;
+            todo &= todo - 1;
             const float xd = __shfl_sync(FS_FULL_MASK, ex[sh], sl);
             const int xj = __shfl_sync(FS_FULL_MASK, sj[sh], sl);
-            const bool xa = __shfl_sync(FS_FULL_MASK, (int)amb[sh], sl) != 0;
-            if (xa) {
 #pragma unroll
-                for (int h = 0; h < H; ++h)
-                    if (amb[h] && fs_pair_less(xd, xj, ex[h], sj[h])) ++rank[h];
-            }
+            for (int h = 0; h < H; ++h)
+                if (amb[h] && fs_pair_less(xd, xj, ex[h], sj[h])) ++rank[h];
         }
     }
 #pragma unroll
@@ -623,23 +660,25 @@ knn_tc_finalize_kernel(const float* __restrict__ x, int ldx, int N, long long P,
     const int q = (int)(row - cloud0);
     const int kk = k + (self_loop ? 0 : 1);
     const int skip = self_loop ? 0 : 1;
-    const int n = __ldg(cand_n + row);
-    if (n > TC_CAP || n < kk) {        // overflow (or a NaN row): the exact kernel redoes this query
+    const int n0 = __ldg(cand_n + row * TC_HALVES), n1 = __ldg(cand_n + row * TC_HALVES + 1);
+    const int n = n0 + n1;
+    const float cmax = __int_as_float(__ldg(norm_max_bits + 2 * b)), rmax = __int_as_float(__ldg(norm_max_bits + 2 * b + 1));
+    const float qq = __ldg(sqnorm + row);
+    const float err = tc_row_err(__ldg(cnorm + row), cmax, qq, rmax);
+    // overflow of a half's list, too few survivors or a NaN row: the exact kernel redoes this query
+    if (n0 > TC_CAP / TC_HALVES || n1 > TC_CAP / TC_HALVES || n < kk || !(err == err)) {
         if (lane == 0) redo[row] = 1;
         return;
     }
     if (lane == 0) redo[row] = 0;
-    const float cmax = __int_as_float(__ldg(norm_max_bits + 2 * b)), rmax = __int_as_float(__ldg(norm_max_bits + 2 * b + 1));
-    const float qq = __ldg(sqnorm + row);
-    const float err = tc_row_err(__ldg(cnorm + row), cmax, qq, rmax);
     if (n <= 32)
-        tc_finalize_row<1>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, cand_j, cand_d, sqnorm, err, qq,
+        tc_finalize_row<1>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, n0, cand_j, cand_d, sqnorm, err, qq,
                            qd_all + warp * 64, qi_all + warp * 64, xq[warp], idx + row * k);
     else if (n <= 64)
-        tc_finalize_row<2>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, cand_j, cand_d, sqnorm, err, qq,
+        tc_finalize_row<2>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, n0, cand_j, cand_d, sqnorm, err, qq,
                            qd_all + warp * 64, qi_all + warp * 64, xq[warp], idx + row * k);
     else
-        tc_finalize_row<4>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, cand_j, cand_d, sqnorm, err, qq,
+        tc_finalize_row<4>(x, ldx, cloud0, q, row, k, kk, skip, diag_zero, n, n0, cand_j, cand_d, sqnorm, err, qq,
                            qd_all + warp * 64, qi_all + warp * 64, xq[warp], idx + row * k);
 }
 
@@ -673,7 +712,8 @@ extern "C" size_t fs_knn_feat_tc_workspace_bytes(int B, int N, int C, int k) {
     size_t bytes = 0;
     bytes += align_up(P * TC_KROW * 2, 256) * 2;        // A', B'
     bytes += align_up(P * TC_CAP * 4, 256) * 2;         // survivor indices, distances
-    bytes += align_up(P * 4, 256) * 3;                  // survivor counts, raw norms, centred norms
+    bytes += align_up(P * 4 * TC_HALVES, 256);          // survivor counts (one per column half)
+    bytes += align_up(P * 4, 256) * 2;                  // raw norms, centred norms
     bytes += align_up((size_t)B * TC_C * 4, 256);       // channel sums
     bytes += align_up((size_t)B * 8, 256);              // max centred / raw norm per cloud
     bytes += align_up(P, 256);                          // redo flags
@@ -704,7 +744,7 @@ extern "C" int fs_knn_feat_tc(int device, fs_stream_t stream_, const float* x, i
     __nv_bfloat16* Bm = reinterpret_cast<__nv_bfloat16*>(ws); ws += align_up((size_t)P * TC_KROW * 2, 256);
     int32_t* cand_j = reinterpret_cast<int32_t*>(ws); ws += align_up((size_t)P * TC_CAP * 4, 256);
     float* cand_d = reinterpret_cast<float*>(ws); ws += align_up((size_t)P * TC_CAP * 4, 256);
-    int32_t* cand_n = reinterpret_cast<int32_t*>(ws); ws += align_up((size_t)P * 4, 256);
+    int32_t* cand_n = reinterpret_cast<int32_t*>(ws); ws += align_up((size_t)P * 4 * TC_HALVES, 256);
     float* sqnorm = reinterpret_cast<float*>(ws); ws += align_up((size_t)P * 4, 256);
     float* cnorm = reinterpret_cast<float*>(ws); ws += align_up((size_t)P * 4, 256);
     float* sums = reinterpret_cast<float*>(ws); ws += align_up((size_t)B * TC_C * 4, 256);

@@ -31,6 +31,45 @@ __device__ __forceinline__ void fs_warp_bitonic_sort(float& d, int& i, int lane)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed 64-bit keys: (order-preserving float bits << 32) | index. With unique indices the keys are unique, so a
+// compare-exchange is one unsigned 64-bit comparison instead of the two-level (distance, index) test.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long fs_pack_key(float d, int i) {
+    const uint32_t b = __float_as_uint(d);
+    const uint32_t o = b ^ ((b & 0x80000000u) ? 0xffffffffu : 0x80000000u);
+    return ((unsigned long long)o << 32) | (uint32_t)i;
+}
+__device__ __forceinline__ void fs_unpack_key(unsigned long long key, float& d, int& i) {
+    const uint32_t o = (uint32_t)(key >> 32);
+    d = __uint_as_float(o ^ ((o & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+    i = (int)(uint32_t)key;
+}
+// Ascending bitonic sort of 32*H keys, element e = h*32 + lane (H = 1 or 2).
+template <int H>
+__device__ __forceinline__ void fs_warp_bitonic_sort_keys(unsigned long long (&key)[H], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * H; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j == 32) {                       // H == 2, final merge: partner is the lane's other element
+                if (key[H - 1] < key[0]) { const unsigned long long t = key[0]; key[0] = key[H - 1]; key[H - 1] = t; }
+            } else {
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const unsigned long long o = __shfl_xor_sync(FS_FULL_MASK, key[h], j);
+                    const int e = h * 32 + lane;
+                    const bool up = (e & k) == 0 || k == 32 * H;
+                    const bool lower = (lane & j) == 0;
+                    const bool keep_min = (lower == up);
+                    if ((o < key[h]) == keep_min) key[h] = o;
+                }
+            }
+        }
+    }
+}
+
 template <int KPL>
 struct FsWarpSelect {
     static_assert(KPL == 1 || KPL == 2 || KPL == 4, "list length must be 32, 64 or 128");
