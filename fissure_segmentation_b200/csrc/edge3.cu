@@ -190,23 +190,31 @@ template <> __device__ __forceinline__ void load_nc<__nv_bfloat16, 4>(const __nv
 // Backward, ONE pass over dH: per channel  s1 = sum d,  s2 = sum d*yhat,  A[a] = sum d * e_a   (d = dH * LeakyReLU'(z)).
 // The BatchNorm-coupled weight gradient then follows in closed form from the edge moments (edge3_dw_kernel).
 // acc layout (float): [Cp][6] A sums (atomics; zeroed by the caller).
+//
+// One warp per point. A dH row (Cp channels) is read by LPRW = Cp/4 lanes with one 8-byte (bf16) or 16-byte (fp32)
+// load each, so a warp-wide load covers EPW = 32/LPRW edges and four such loads are in flight per lane
+// (1 KB per warp); the first revision used 4-byte loads of one edge at a time and was latency bound at 0.8 TB/s.
 template <typename GT, int CP>
 __global__ void __launch_bounds__(E3_THREADS)
 edge3_bwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ idx, long long P, int N, int k,
                  const float* __restrict__ w, const float* __restrict__ coef, const GT* __restrict__ dh, double* __restrict__ dgb,
                  float* __restrict__ acc_out) {
-    constexpr int NC = CP / 32;
+    constexpr int NC = 4;
+    constexpr int LPRW = CP / NC;          // lanes per dH row (16 or 32)
+    constexpr int EPW = 32 / LPRW;         // edges per warp-wide load (2 or 1)
+    constexpr int U = 4;                   // loads in flight per lane
+    static_assert(LPRW <= 32 && EPW * LPRW == 32, "Cp must be 64 or 128");
     __shared__ double red[2 * NC * E3_THREADS];
     __shared__ float ared[E3_THREADS / 32][CP * 6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = lane * NC;
-    float wr[NC][6], mu[NC], inv[NC], sc[NC], be[NC];
+    const int sub = lane / LPRW;
+    const int c0 = (lane % LPRW) * NC;
+    float wr[NC][6], mu[NC], sc[NC], be[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
 #pragma unroll
         for (int a = 0; a < 6; ++a) wr[i][a] = __ldg(w + (c0 + i) * 6 + a);
-        mu[i] = __ldg(coef + c0 + i); inv[i] = __ldg(coef + CP + c0 + i);
-        sc[i] = __ldg(coef + 2 * CP + c0 + i); be[i] = __ldg(coef + 3 * CP + c0 + i);
+        mu[i] = __ldg(coef + c0 + i); sc[i] = __ldg(coef + 2 * CP + c0 + i); be[i] = __ldg(coef + 3 * CP + c0 + i);
     }
     float s1[NC], s2[NC], A[NC][6];
 #pragma unroll
@@ -227,26 +235,29 @@ edge3_bwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict
             const long long jl = cloud0 + __ldg(idx + pt * k + tl);
             const float n0 = __ldg(x + jl * ldx), n1 = __ldg(x + jl * ldx + 1), n2 = __ldg(x + jl * ldx + 2);
             const int tn = k - t0 < 32 ? k - t0 : 32;
-            for (int tb = 0; tb < tn; tb += 4) {
-                float g[4][NC];
+            for (int tb = 0; tb < tn; tb += EPW * U) {
+                float g[U][NC];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {       // four independent dH row loads in flight
-                    const int tt = tb + u < tn ? tb + u : tn - 1;
-                    load_nc<GT, NC>(dh + (pt * k + t0 + tt) * CP + c0, g[u]);
+                for (int u = 0; u < U; ++u) {
+                    const int tt = tb + u * EPW + sub;
+                    load_nc<GT, NC>(dh + (pt * k + t0 + (tt < tn ? tt : tn - 1)) * CP + c0, g[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (tb + u < tn) {
-                        const int tt = tb + u;
-                        const float d0 = __shfl_sync(FS_FULL_MASK, n0, tt) - xi0, d1 = __shfl_sync(FS_FULL_MASK, n1, tt) - xi1,
-                                    d2 = __shfl_sync(FS_FULL_MASK, n2, tt) - xi2;
+                for (int u = 0; u < U; ++u) {
+                    if (tb + u * EPW < tn) {                     // warp-uniform
+                        const int tt = tb + u * EPW + sub;
+                        const int ts = tt < tn ? tt : tn - 1;
+                        const float live = tt < tn ? 1.f : 0.f;      // the clamped duplicate contributes nothing
+                        const float d0 = __shfl_sync(FS_FULL_MASK, n0, ts) - xi0, d1 = __shfl_sync(FS_FULL_MASK, n1, ts) - xi1,
+                                    d2 = __shfl_sync(FS_FULL_MASK, n2, ts) - xi2;
 #pragma unroll
                         for (int i = 0; i < NC; ++i) {
                             const float y = fmaf(wr[i][2], d2, fmaf(wr[i][1], d1, fmaf(wr[i][0], d0, base[i])));
                             const float yc = y - mu[i];
                             const float z = fmaf(sc[i], yc, be[i]);
-                            const float d = z > 0.f ? g[u][i] : 0.2f * g[u][i];
-                            s2[i] = fmaf(d, yc * inv[i], s2[i]);
+                            const float gl = g[u][i] * live;
+                            const float d = z > 0.f ? gl : 0.2f * gl;
+                            s2[i] = fmaf(d, yc, s2[i]);
                             dsum[i] += d;
                             A[i][0] = fmaf(d, d0, A[i][0]); A[i][1] = fmaf(d, d1, A[i][1]); A[i][2] = fmaf(d, d2, A[i][2]);
                         }
@@ -260,15 +271,32 @@ edge3_bwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict
             A[i][3] = fmaf(dsum[i], xi0, A[i][3]); A[i][4] = fmaf(dsum[i], xi1, A[i][4]); A[i][5] = fmaf(dsum[i], xi2, A[i][5]);
         }
     }
+    // the EPW edge sub-groups of a warp own the same channels: fold them into sub-group 0
 #pragma unroll
-    for (int i = 0; i < NC; ++i)
+    for (int o = LPRW; o < 32; o <<= 1) {
 #pragma unroll
-        for (int a = 0; a < 6; ++a) ared[warp][(c0 + i) * 6 + a] = A[i][a];
+        for (int i = 0; i < NC; ++i) {
+            s1[i] += __shfl_xor_sync(FS_FULL_MASK, s1[i], o);
+            s2[i] += __shfl_xor_sync(FS_FULL_MASK, s2[i], o);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) A[i][a] += __shfl_xor_sync(FS_FULL_MASK, A[i][a], o);
+        }
+    }
+    if (sub == 0) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+#pragma unroll
+            for (int a = 0; a < 6; ++a) ared[warp][(c0 + i) * 6 + a] = A[i][a];
+    }
     double d1v[NC], d2v[NC];
     int chans[NC];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) { d1v[i] = (double)s1[i]; d2v[i] = (double)s2[i]; chans[i] = c0 + i; }
-    fs_stats_commit<NC>(red, d1v, d2v, chans, 32, CP, dgb);      // contains the __syncthreads that publishes ared
+    for (int i = 0; i < NC; ++i) {
+        d1v[i] = sub == 0 ? (double)s1[i] : 0.0;
+        d2v[i] = sub == 0 ? (double)s2[i] * (double)__ldg(coef + CP + c0 + i) : 0.0;     // yhat = yc * invstd
+        chans[i] = c0 + i;
+    }
+    fs_stats_commit<NC>(red, d1v, d2v, chans, LPRW, CP, dgb);     // contains the __syncthreads that publishes ared
     for (int o = threadIdx.x; o < CP * 6; o += E3_THREADS) {
         float v = 0.f;
 #pragma unroll

@@ -28,13 +28,15 @@ class FlatDataParallel:
         self.flat_param = torch.empty(total, dtype=dt, device=dev)
         self.flat_grad = torch.zeros(total, dtype=dt, device=dev)
         self._slices = []
+        self._grad_views = []
         off = 0
         with torch.no_grad():
             for p in order:
                 n = p.numel()
                 self.flat_param[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_param[off:off + n].view_as(p)
-                p.grad = self.flat_grad[off:off + n].view_as(p)
+                self._grad_views.append(self.flat_grad[off:off + n].view_as(p))
+                p.grad = None
                 self._slices.append((off, n))
                 off += n
         self.params = order
@@ -42,54 +44,76 @@ class FlatDataParallel:
         n_buckets = max(1, min(n_buckets, len(order)))
         target = total / n_buckets
         self.buckets = []          # (start, end, n_params)
+        self._bucket_members = []  # parameter positions of every bucket
         self._bucket_of = {}
-        start, count, b = 0, 0, 0
+        start, count, b, first = 0, 0, 0, 0
         for i, (o, n) in enumerate(self._slices):
             self._bucket_of[id(order[i])] = b
             count += 1
             end = o + n
             if (end - start >= target and b < n_buckets - 1) or i == len(order) - 1:
                 self.buckets.append((start, end, count))
-                start, count, b = end, 0, b + 1
+                self._bucket_members.append(list(range(first, i + 1)))
+                start, count, b, first = end, 0, b + 1, i + 1
         self._ready = [0] * len(self.buckets)
+        self._sent = [False] * len(self.buckets)
         self._works = []
+        if self.world > 1 and broadcast:
+            dist.broadcast(self.flat_param, src=0, group=self.group)
+        # Gradients are NOT accumulated into the flat buffer by autograd (that costs one add kernel per parameter
+        # and a memset per step): zero_grad() drops them, autograd assigns the fresh tensors, and when the last
+        # gradient of a bucket has arrived ONE multi-tensor copy moves the bucket into the flat buffer, followed by
+        # its asynchronous all-reduce.
+        for p in order:
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    def _flush(self, b):
+        s, e, _ = self.buckets[b]
+        src, dst, missing = [], [], False
+        for i in self._bucket_members[b]:
+            g = self.params[i].grad
+            if g is None:
+                missing = True
+            elif g.data_ptr() != self._grad_views[i].data_ptr():
+                src.append(g)
+                dst.append(self._grad_views[i])
+        if missing:                 # parameters without a gradient this step count as zero
+            self.flat_grad[s:e].zero_()
+        if src:
+            torch._foreach_copy_(dst, src)
+        for i in self._bucket_members[b]:
+            if self.params[i].grad is not None:
+                self.params[i].grad = self._grad_views[i]          # .grad shows the (to be) reduced gradient
+        self._sent[b] = True
         if self.world > 1:
-            if broadcast:
-                dist.broadcast(self.flat_param, src=0, group=self.group)
-            for p in order:
-                p.register_post_accumulate_grad_hook(self._hook)
+            self._works.append(dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.SUM, group=self.group,
+                                               async_op=True))
 
     def _hook(self, p):
         b = self._bucket_of[id(p)]
         self._ready[b] += 1
-        if self._ready[b] == self.buckets[b][2]:
-            s, e, _ = self.buckets[b]
-            self._works.append(dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.SUM, group=self.group,
-                                               async_op=True))
+        if self._ready[b] == self.buckets[b][2] and not self._sent[b]:
+            self._flush(b)
 
     def __call__(self, *args, **kwargs):
         return self.module(*args, **kwargs)
 
     def zero_grad(self):
-        self.flat_grad.zero_()
-        for p in self.params:      # keep the views attached even if something set .grad to None
-            if p.grad is None:
-                o, n = self._slices[self.params.index(p)]
-                p.grad = self.flat_grad[o:o + n].view_as(p)
+        for p in self.params:
+            p.grad = None
 
     def finish_backward(self):
-        """Wait for the outstanding bucket all-reduces; flat_grad then holds the SUM over ranks
-        (the 1/world average is folded into the optimiser's grad_scale)."""
-        if self.world > 1 and sum(self._ready) != sum(b[2] for b in self.buckets):
-            # parameters that received no gradient this step: reduce whatever has not been sent
-            for b, (s, e, cnt) in enumerate(self.buckets):
-                if self._ready[b] != cnt:
-                    self._works.append(dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.SUM, group=self.group,
-                                                       async_op=True))
+        """Flush the buckets whose parameters did not all receive a gradient, wait for the outstanding bucket
+        all-reduces; flat_grad then holds the SUM over ranks (the 1/world average is folded into the optimiser's
+        grad_scale)."""
+        for b in range(len(self.buckets)):
+            if not self._sent[b]:
+                self._flush(b)
         for w in self._works:
             w.wait()
         self._works = []
         self._ready = [0] * len(self.buckets)
+        self._sent = [False] * len(self.buckets)
 
 
 class FlatAdam:

@@ -312,6 +312,7 @@ class DGCNNBase(PointSegmentationModelBase):
 
     def forward(self, x):
         self._perm = None
+        ops.begin_step(x.device)      # one zero-filled arena for all statistics buffers of this step
         if self.spatial_sort and x.is_cuda and x.shape[1] >= 3:
             with torch.no_grad():
                 self._perm = ops.spatial_order(x.detach())

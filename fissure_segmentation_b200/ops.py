@@ -115,9 +115,52 @@ def knn_any(x, k, self_loop=False, diag_zero=True, return_dist=False):
 
 # ------------------------------------------------------------------------------------------- EdgeConv
 
+class _ZeroArena:
+    """Zero-filled fp64 scratch shared by all per-layer statistics buffers of one training step: ONE memset per
+    step instead of one fill kernel per BatchNorm layer and direction (16 launches in DGCNNSeg). The networks
+    call `begin_step` at the top of forward(); the capacity follows the demand of the previous step, anything
+    beyond it (first step, stand-alone layers) falls back to an individual torch.zeros."""
+
+    def __init__(self):
+        self.buf, self.off, self.cap, self.demand = None, 0, 0, 0
+
+    def begin_step(self, device):
+        self.cap = max(self.cap, self.demand)
+        self.demand, self.off = 0, 0
+        self.buf = torch.zeros(self.cap, dtype=torch.float64, device=device) if self.cap else None
+
+    def take(self, n, device):
+        n = (n + 1) & ~1                      # keep 16-byte alignment of every slice
+        self.demand += n
+        if self.buf is not None and self.buf.device == device and self.off + n <= self.cap:
+            out = self.buf[self.off:self.off + n]
+            self.off += n
+            return out
+        return torch.zeros(n, dtype=torch.float64, device=device)
+
+
+_arenas = {}
+
+
+def begin_step(device):
+    """Start a new zero-filled statistics arena on `device` (called by the networks' forward)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        return
+    _arenas.setdefault(device, _ZeroArena()).begin_step(device)
+
+
+def _zeros64(n, device):
+    """n zero-filled 8-byte words (fp64 view) from the step arena."""
+    arena = _arenas.get(torch.device(device))
+    if arena is None:
+        return torch.zeros(n, dtype=torch.float64, device=device)
+    return arena.take(n, torch.device(device))
+
+
 def _stats_buffer(C, device):
     """Zero-filled fp64 statistics buffer (final sums | pivot | slot partials | ticket) for C channels."""
-    return torch.zeros(_lib.load().fs_stats_buffer_doubles(C), dtype=torch.float64, device=device)
+    return _zeros64(_lib.load().fs_stats_buffer_doubles(C), device)
 
 
 def _bn_coef(table_ref, stats, count, gamma, beta, running_mean, running_var, nbt, training, Cp, eps, momentum):
@@ -393,7 +436,7 @@ class _PoolBnActFn(torch.autograd.Function):
         sel = torch.empty(B, C, dtype=torch.float32, device=dev)
         arg = torch.empty(B, C, dtype=torch.int32, device=dev)
         stats = _stats_buffer(C, dev) if training else None
-        packed = torch.zeros(B * C, dtype=torch.int64, device=dev)
+        packed = _zeros64(B * C, dev).view(torch.int64)
         _lib.call("fs_pool_reduce", x, x, _lib.dtype_code(x), x.stride(0), B, N, C, gamma32, sel, arg, stats, packed)
         coef = _bn_coef(x, stats, B * N, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
         out = torch.empty(B, C, dtype=x.dtype, device=dev)
@@ -475,7 +518,7 @@ class _EdgeFirst3Fn(torch.autograd.Function):
         coef = torch.empty(4 * Cp, dtype=torch.float32, device=dev)
         mom = None
         if training:
-            mom = torch.zeros(_lib.load().fs_edge3_moment_doubles(), dtype=torch.float64, device=dev)
+            mom = _zeros64(_lib.load().fs_edge3_moment_doubles(), dev)
             _lib.call("fs_edge3_bn_coef", x, x, x.stride(0), graph.idx, B, N, k, w32, Cp, gamma32, beta32, eps, momentum,
                       mom, coef, running_mean, running_var, nbt)
         else:
@@ -497,7 +540,7 @@ class _EdgeFirst3Fn(torch.autograd.Function):
             dh = dh.float()
         dh = dh.contiguous()
         dgb = _stats_buffer(Cp, x.device)
-        acc = torch.zeros(Cp, 6, dtype=torch.float32, device=x.device)
+        acc = _zeros64(Cp * 3, x.device).view(torch.float32).view(Cp, 6)
         dw = torch.empty(Cp, 6, dtype=torch.float32, device=x.device)
         _lib.call("fs_edge3_bwd", x, x, x.stride(0), graph.idx, B, N, k, w32, Cp, coef, dh, _lib.dtype_code(dh),
                   int(ctx.training), mom, dgb, acc, dw)
