@@ -342,55 +342,64 @@ __global__ void pool_decode_kernel(const unsigned long long* __restrict__ packed
 }
 
 // dX[r, c] = scale * ( [r == arg[b,c]] * d[b,c] - dbeta/M - xhat[r,c] * dgamma/M ),  d = g * LeakyReLU'(z_sel)
+// grid (row chunks, clouds): the cloud of a CTA is fixed, so the arg-max row and the routed gradient of the
+// thread's channels are loaded ONCE into registers (the first revision re-read arg per element and divided by N per
+// row); four independent row loads are in flight per thread.
 template <typename T, typename OT>
 __global__ void __launch_bounds__(DN_THREADS)
 pool_bwd_kernel(const T* __restrict__ x, int ld, int N, long long rows, int C, const float* __restrict__ g,
                 const float* __restrict__ sel, const int32_t* __restrict__ arg, const float* __restrict__ coef, float slope,
                 const double* __restrict__ dgb, double count, int train_stats, OT* __restrict__ dx, int ld_dx) {
     constexpr int V = Vec<T>::N;
+    constexpr int U = 4;
     RowMap m(C, V);
     const int cc = m.c0;
-    float mu[V], sc[V], mb[V], mg[V];
+    const long long b = blockIdx.y;
+    float mu[V], sc[V], mb[V], mg[V], routed[V];
+    int ar[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
         mu[i] = __ldg(coef + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i);
         mb[i] = train_stats ? (float)(dgb[cc + i] / count) : 0.f;
         mg[i] = train_stats ? (float)(dgb[C + cc + i] / count) * __ldg(coef + C + cc + i) : 0.f;
+        ar[i] = __ldg(arg + b * C + cc + i);
+        const float zs = fmaf(sc[i], __ldg(sel + b * C + cc + i) - mu[i], __ldg(coef + 3 * C + cc + i));
+        const float gv = __ldg(g + b * C + cc + i);
+        routed[i] = zs > 0.f ? gv : slope * gv;
     }
-    const long long step = (long long)gridDim.x * m.rows_per_pass;
-    for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += 2 * step) {
-        float f[2][V];
-        const bool two = row + step < rows;
-        Vec<T>::load(x + row * ld + cc, f[0]);
-        if (two) Vec<T>::load(x + (row + step) * ld + cc, f[1]);
+    const int step = gridDim.x * m.rows_per_pass;
+    const T* xb = x + b * N * (long long)ld + cc;
+    OT* db = dx + b * N * (long long)ld_dx + cc;
+    for (int r0 = blockIdx.x * m.rows_per_pass + m.r; r0 < N; r0 += U * step) {
+        float f[U][V];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !two) break;
-            const long long rr = row + u * step;
-            const long long b = rr / N;
-            const int r = (int)(rr - b * N);
-            float o[V];
+        for (int u = 0; u < U; ++u) {
+            const int r = r0 + u * step;
+            Vec<T>::load(xb + (long long)(r < N ? r : r0) * ld, f[u]);
+        }
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                float routed = 0.f;
-                if (__ldg(arg + b * C + cc + i) == r) {
-                    const float zs = fmaf(sc[i], __ldg(sel + b * C + cc + i) - mu[i], __ldg(coef + 3 * C + cc + i));
-                    const float gv = __ldg(g + b * C + cc + i);
-                    routed = zs > 0.f ? gv : slope * gv;
+        for (int u = 0; u < U; ++u) {
+            const int r = r0 + u * step;
+            if (r < N) {
+                float o[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float rt = ar[i] == r ? routed[i] : 0.f;
+                    o[i] = train_stats ? sc[i] * (rt - mb[i] - mg[i] * (f[u][i] - mu[i])) : sc[i] * rt;
                 }
-                o[i] = train_stats ? sc[i] * (routed - mb[i] - mg[i] * (f[u][i] - mu[i])) : sc[i] * routed;
-            }
-            if (V == 8 && sizeof(OT) == 4) {
-                Vec<float>::store(reinterpret_cast<float*>(dx) + rr * ld_dx + cc, o);
-                Vec<float>::store(reinterpret_cast<float*>(dx) + rr * ld_dx + cc + 4, o + 4);
-            } else if (V == 4 && sizeof(OT) == 2) {
-                uint2 v;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
-                h[0] = __floats2bfloat162_rn(o[0], o[1]);
-                h[1] = __floats2bfloat162_rn(o[2], o[3]);
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dx) + rr * ld_dx + cc) = v;
-            } else {
-                Vec<OT>::store(dx + rr * ld_dx + cc, o);
+                OT* op = db + (long long)r * ld_dx;
+                if (V == 8 && sizeof(OT) == 4) {
+                    Vec<float>::store(reinterpret_cast<float*>(op), o);
+                    Vec<float>::store(reinterpret_cast<float*>(op) + 4, o + 4);
+                } else if (V == 4 && sizeof(OT) == 2) {
+                    uint2 v;
+                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+                    h[0] = __floats2bfloat162_rn(o[0], o[1]);
+                    h[1] = __floats2bfloat162_rn(o[2], o[3]);
+                    *reinterpret_cast<uint2*>(op) = v;
+                } else {
+                    Vec<OT>::store(op, o);
+                }
             }
         }
     }
@@ -504,7 +513,12 @@ extern "C" int fs_pool_bwd(int device, fs_stream_t stream_, const void* x, int d
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long rows = (long long)B * N;
-    const int grid = dn_grid(rows, rows_per_pass(C, vec));
+    const int rpp = rows_per_pass(C, vec);
+    int chunks = (8 * FS_NUM_SMS + B - 1) / B;           // about eight blocks per SM in total
+    if (chunks > (N + 4 * rpp - 1) / (4 * rpp)) chunks = (N + 4 * rpp - 1) / (4 * rpp);
+    if (chunks < 1) chunks = 1;
+    if (B > 65535) return FS_ERR_UNSUPPORTED;
+    const dim3 grid(chunks, B);
 #define GO(T, OT) pool_bwd_kernel<<<grid, DN_THREADS, 0, stream>>>((const T*)x, ld, N, rows, C, g, sel, arg, coef, slope, dgb, count, train_stats, (OT*)dx, ld_dx)
     if (dtype == FS_BF16 && dx_dtype == FS_BF16) GO(__nv_bfloat16, __nv_bfloat16);
     else if (dtype == FS_BF16) GO(__nv_bfloat16, float);
