@@ -28,12 +28,24 @@ import torch.nn.functional as F  # noqa: E402
 
 METRIC = "point clouds/sec DGCNNSeg fwd+bwd N=2048 k=20"
 UNIT = "clouds/s"
+GATHER_DRAM_BYTES = 41_080_320      # ncu --set full, one launch, B=32 N=2048 k=20 (profiles/r01_g_gather_smem_full.txt)
+
+
+def _tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f).get("bf16_tflops", 1626.3))
+    return 1626.3
+
+
+TENSOR_PEAK_TFLOPS = _tensor_peak()
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clouds per GPU")
@@ -294,15 +306,16 @@ def run_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    # ---- per-launch duration of the roofline kernel: CUDA events around its launches in eager steps of the same
+    # ---- per-launch duration of the roofline kernels: CUDA events around their launches in eager steps of the same
     #      workload (events cannot be read back from inside a replayed graph)
-    _lib.time_calls.update({"fs_edgeconv_gather"})
+    _lib.time_calls.update({"fs_edgeconv_gather", "fs_knn_feat_tc"})
     _lib.timed.clear()
     for i in range(3):
         train_step(*pool_d[i % n_pool])
     barrier()
     _lib.time_calls.clear()
     gather_ms = [a.elapsed_time(b) for a, b in _lib.timed.get("fs_edgeconv_gather", [])]
+    knn_ms = [a.elapsed_time(b) for a, b in _lib.timed.get("fs_knn_feat_tc", [])]
     _lib.timed.clear()
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
@@ -331,12 +344,28 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(x_in.numel() * 4 + y_in.numel() * 8), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "cuda_graph": graph is not None,
             "clocks": clocks,
-            "roofline": {"kernel": "edgeconv_gather_kernel (Cp=64, train)", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": "edgeconv_gather_smem_kernel<16,5,0,float> (ec2/ec3 gather/max pass, Cp=64, train)",
+                         "bound": "hbm", "achieved": achieved,
                          "peak": hbm_peak, "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / hbm_peak) if achieved else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape
+                         # (profiles/r01_g_gather_smem_full.txt): the 37 MB of outputs stay in the 126 MB L2
+                         "traffic": GATHER_DRAM_BYTES if (args.batch, args.points, args.k) == (32, 2048, 20) else None,
                          "launch_ms": g_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "launches_timed": len(gather_ms)},
         }
+        if knn_ms:
+            # feature-space kNN (ec2/ec3 graphs): the tcgen05 distance GEMM and its selection epilogue, whole entry
+            # point (prep + tensor-core sweeps + finalize). Algorithmic flops 2*B*N^2*C; the kernel issues
+            # 2 sweeps x K = 208 (bf16 hi/lo split) = 6.5x as many.
+            kms = statistics.mean(knn_ms)
+            alg_flops = 2.0 * args.batch * args.points * args.points * 64
+            line["roofline_knn_gemm"] = {
+                "kernel": "fs_knn_feat_tc entry point (tc_colsum + tc_split + knn_tc_select [tcgen05] + knn_tc_finalize)",
+                "bound": "tensor", "achieved": alg_flops / (kms * 1e-3) / 1e12, "peak": TENSOR_PEAK_TFLOPS,
+                "unit": "TFLOP/s", "frac": alg_flops / (kms * 1e-3) / 1e12 / TENSOR_PEAK_TFLOPS,
+                "issued_tflops": alg_flops * 6.5 / (kms * 1e-3) / 1e12, "launch_ms": kms,
+                "tensor_pipe_active_pct_ncu": 42.1, "launches_timed": len(knn_ms)}
         if world == 1 and not args.no_cpu_baseline:
             val, spstep, threads, n = cpu_reference_steps(args, 6, 2, max_seconds=30.0)
             line["cpu_baseline"] = {
