@@ -374,7 +374,17 @@ def run_ours(args):
                           "reference's PyTorch CPU path, fp32)" % (args.cpu_batch, n, args.points, args.k)}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: the captured CUDA graph holds NCCL work of this communicator, and destroying the process group
+        # (or letting the interpreter finalise it) while the graph is alive has been seen to dead-lock after the
+        # result line was printed. Drop the graph, drain the device, meet the other ranks once more and leave
+        # without running the NCCL / CUDA finalisers.
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -178,3 +178,43 @@ def test_two_layer_edgeconv_on_coordinates_vs_oracle(lib, widths, N, k):
     for n, v in stats.items():
         assert_close(ec.state_dict()[n[3:]], v, 1e-4, 1e-6, n)
     assert int(ec.state_dict()["shared_mlp.0.layers.1.num_batches_tracked"]) == 1
+
+
+@pytest.mark.parametrize("B,N,k,Cp", [(2, 256, 8, 64), (32, 256, 8, 64), (2, 2048, 20, 64), (3, 1000, 20, 64),
+                                      (2, 4096, 40, 64), (1, 8192, 40, 64), (3, 700, 7, 128), (2, 300, 33, 256)])
+def test_smem_gather_is_bit_identical_to_global_gather(lib, B, N, k, Cp):
+    """The shared-memory-resident gather (edgeconv_smem.cu: channel-sliced table per CTA, cp.async index staging,
+    small-batch point split, N = 8192 falls back) must reproduce the global-memory kernel: sel / arg / eval outputs
+    bit for bit, the edge sums and the fp64 statistics up to summation order."""
+    import os
+    from fissure_segmentation_b200 import _lib
+    torch.manual_seed(B * 1000 + N + k)
+    P = B * N
+    idx = torch.stack([torch.stack([torch.randperm(N, device=DEV)[:k] for _ in range(N)]) for _ in range(B)]).int().contiguous()
+    rev_ptr, _ = ops.KnnGraph(idx).reverse()
+    table = torch.randn(P, 2 * Cp, device=DEV)
+    gamma = torch.randn(Cp, device=DEV)             # both signs: max and min channels
+    coef = torch.randn(4 * Cp, device=DEV)
+    res = {}
+    try:
+        for mode in ("global", "smem"):
+            os.environ["FS_GATHER"] = mode
+            sel = torch.empty(P, Cp, device=DEV)
+            arg = torch.empty(P, Cp, dtype=torch.uint8, device=DEV)
+            sy = torch.empty(P, Cp, device=DEV)
+            st = torch.zeros(_lib.load().fs_stats_buffer_doubles(Cp), dtype=torch.float64, device=DEV)
+            _lib.call("fs_edgeconv_gather", table, table, 0, table.stride(0), idx, B, N, k, Cp, gamma, rev_ptr, sel, arg, sy, st)
+            out = torch.empty(P, Cp, device=DEV)
+            out16 = torch.empty(P, Cp, device=DEV, dtype=torch.bfloat16)
+            arg2 = torch.empty_like(arg)
+            _lib.call("fs_edgeconv_fused_eval", table, table, 0, table.stride(0), idx, B, N, k, Cp, coef, out, 0, out.stride(0), arg2)
+            _lib.call("fs_edgeconv_fused_eval", table, table, 0, table.stride(0), idx, B, N, k, Cp, coef, out16, 1, out16.stride(0), None)
+            torch.cuda.synchronize()
+            res[mode] = (sel, arg, sy, st[:3 * Cp].clone(), out, arg2, out16)
+    finally:
+        os.environ.pop("FS_GATHER", None)
+    a, b = res["global"], res["smem"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])                    # selected value and slot
+    assert torch.equal(a[4], b[4]) and torch.equal(a[5], b[5]) and torch.equal(a[6], b[6])   # eval mode
+    assert torch.allclose(a[2], b[2], rtol=1e-5, atol=1e-5)                       # sum over the k neighbours
+    assert torch.allclose(a[3], b[3], rtol=1e-6, atol=1e-6)                       # fp64 batch statistics + pivots

@@ -64,7 +64,8 @@ def test_knn3d_lattice_tie_report(golden, lib):
     assert rep["mismatch_rows"] <= rep["tie_rows"]
 
 
-@pytest.mark.parametrize("C,N,k", [(64, 2048, 20), (128, 512, 40), (9, 700, 8), (256, 300, 16), (64, 4096, 40)])
+@pytest.mark.parametrize("C,N,k", [(64, 2048, 20), (128, 512, 40), (9, 700, 8), (256, 300, 16), (64, 4096, 40),
+                                   (64, 1000, 32), (64, 200, 5), (64, 2048, 31)])
 def test_knn_feature_space_exact(C, N, k, lib):
     gen = torch.Generator().manual_seed(C * 7 + N)
     feat = torch.randn(2, C, N, generator=gen)

@@ -105,3 +105,55 @@ def test_pointops_cuda_module_importable():
                  "subtraction_forward_cuda", "subtraction_backward_cuda", "aggregation_forward_cuda",
                  "aggregation_backward_cuda", "interpolation_forward_cuda", "interpolation_backward_cuda"):
         assert callable(getattr(pointops_cuda, name))
+
+
+def test_flat_data_parallel_single_process_semantics():
+    """world size 1, CPU: gradients are moved bucket-wise into the flat buffer (no per-parameter accumulation),
+    parameters that received no gradient count as zero, `.grad` views the flat buffer after the step."""
+    from fissure_segmentation_b200.ddp import FlatDataParallel
+    torch.manual_seed(3)
+    used = torch.nn.Linear(5, 4)
+    unused = torch.nn.Linear(5, 2)                       # never part of the loss: no gradient arrives
+    net = torch.nn.ModuleDict({"used": used, "unused": unused})
+    dp = FlatDataParallel(net, n_buckets=2)
+    x = torch.randn(7, 5)
+    for step in range(2):                                # second step: stale gradients must not leak
+        dp.zero_grad()
+        assert all(p.grad is None for p in dp.params)
+        (used(x) ** 2).sum().backward()
+        dp.finish_backward()
+    ref = torch.nn.Linear(5, 4)
+    ref.load_state_dict(used.state_dict())
+    (ref(x) ** 2).sum().backward()
+    got = {id(p): dp.flat_grad[o:o + n].view_as(p) for p, (o, n) in zip(dp.params, dp._slices)}
+    assert torch.allclose(got[id(used.weight)], ref.weight.grad) and torch.allclose(got[id(used.bias)], ref.bias.grad)
+    assert float(got[id(unused.weight)].abs().max()) == 0.0 and float(got[id(unused.bias)].abs().max()) == 0.0
+    assert used.weight.grad.data_ptr() == got[id(used.weight)].data_ptr()      # .grad is the flat view
+    # parameters are views of one flat buffer: an in-place update of the buffer moves the module's weights
+    before = used.weight.detach().clone()
+    dp.flat_param.add_(1.0)
+    assert torch.allclose(used.weight.detach(), before + 1.0)
+
+
+def test_statistics_arena_is_zero_filled_and_grows():
+    """ops._ZeroArena: slices are disjoint, zero, 16-byte aligned; demand beyond the capacity falls back to a
+    private buffer and enlarges the next step's arena (one memset per step instead of one per BatchNorm layer)."""
+    from fissure_segmentation_b200 import ops
+    ar = ops._ZeroArena()
+    dev = torch.device("cpu")
+    ar.begin_step(dev)                                   # first step: no capacity yet, every take() is private
+    a = ar.take(5, dev)
+    b = ar.take(8, dev)
+    assert a.numel() == 6 and b.numel() == 8 and ar.buf is None
+    a.fill_(1.0)
+    ar.begin_step(dev)                                   # capacity follows the previous demand (6 + 8)
+    assert ar.cap == 14 and ar.buf.numel() == 14 and float(ar.buf.abs().max()) == 0.0
+    c = ar.take(5, dev)
+    d = ar.take(8, dev)
+    assert c.data_ptr() == ar.buf.data_ptr() and d.data_ptr() == ar.buf.data_ptr() + 6 * 8
+    c.fill_(2.0)
+    assert float(d.abs().max()) == 0.0                   # disjoint slices
+    e = ar.take(4, dev)                                  # beyond the capacity: private zero buffer
+    assert e.data_ptr() != ar.buf.data_ptr() and float(e.abs().max()) == 0.0
+    ar.begin_step(dev)
+    assert ar.cap == 18 and float(ar.buf.abs().max()) == 0.0

@@ -1,3 +1,5 @@
+"""Shape sweep: the shared-memory-resident gather (edgeconv_smem.cu) against the global-memory gather (edgeconv.cu),
+train and eval entry points, bit-exact sel / arg / out. Run on a GPU box: python tools/check_gather_variants.py"""
 import os, sys, torch
 sys.path.insert(0, '.')
 from fissure_segmentation_b200 import ops, _lib
@@ -7,13 +9,13 @@ for (B,N,k,Cp) in [(2,256,8,64),(2,256,20,64),(32,256,8,64),(2,2048,20,64),(3,10
     P=B*N
     idx=torch.stack([torch.stack([torch.randperm(N,device=dev)[:k] for _ in range(N)]) for _ in range(B)]).int().contiguous()
     g=ops.KnnGraph(idx); rev_ptr,_=g.reverse()
-    table=torch.randn(P,2*Cp,device=dev); gamma=torch.randn(Cp,device=dev)
+    table=torch.randn(P,2*Cp,device=dev); gamma=torch.randn(Cp,device=dev); coef=torch.randn(4*Cp,device=dev)
     res={}
     for mode in ('global','smem'):
         os.environ['FS_GATHER']=mode
         sel=torch.empty(P,Cp,device=dev); arg=torch.empty(P,Cp,dtype=torch.uint8,device=dev); sy=torch.empty(P,Cp,device=dev); st=ops._stats_buffer(Cp,dev)
         _lib.call("fs_edgeconv_gather", table, table, 0, table.stride(0), idx, B, N, k, Cp, gamma, rev_ptr, sel, arg, sy, st)
-        coef=torch.randn(4*Cp,device=dev); out=torch.empty(P,Cp,device=dev); outb=torch.empty(P,Cp,device=dev,dtype=torch.bfloat16); arg2=torch.empty_like(arg)
+        out=torch.empty(P,Cp,device=dev); outb=torch.empty(P,Cp,device=dev,dtype=torch.bfloat16); arg2=torch.empty_like(arg)
         _lib.call("fs_edgeconv_fused_eval", table, table, 0, table.stride(0), idx, B, N, k, Cp, coef, out, 0, out.stride(0), arg2)
         _lib.call("fs_edgeconv_fused_eval", table, table, 0, table.stride(0), idx, B, N, k, Cp, coef, outb, 1, outb.stride(0), None)
         torch.cuda.synchronize()

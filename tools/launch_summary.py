@@ -1,3 +1,5 @@
+"""Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel name.
+    python tools/launch_summary.py gpurun_out/launches.csv [top] [steps]"""
 import csv, collections, re, sys
 path = sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/launches.csv'
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25

@@ -1,3 +1,5 @@
+"""Print the key metrics of every kernel in an .ncu-rep (ncu --set full) capture.
+    python tools/ncu_key.py gpurun_out/full_gather.ncu-rep [extra metric substrings]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
 out = subprocess.run(['ncu','-i',rep,'--page','raw','--csv'],capture_output=True,text=True).stdout

@@ -1,3 +1,4 @@
+"""Four feature-space kNN builds at the bench shape (target of the ncu captures of the tcgen05 path)."""
 import sys, torch
 sys.path.insert(0, '.')
 from fissure_segmentation_b200 import ops, synth
