@@ -77,6 +77,29 @@ def test_knn_feature_space_exact(C, N, k, lib):
     assert torch.allclose(d.cpu().sort(-1)[0], ref_d.sort(-1)[0], rtol=1e-4, atol=2e-4 * float(ref_d.max()))
 
 
+@pytest.mark.parametrize("N,k,self_loop", [(2048, 20, True), (2048, 20, False), (1000, 20, True), (200, 5, True),
+                                            (2048, 31, True), (1024, 31, False), (4096, 24, True)])
+def test_knn_tensor_core_path_exact(N, k, self_loop, lib):
+    """The tcgen05 path itself (no distances requested): 64-channel features, two tensor-core sweeps with the
+    64-class bound, survivor lists per column half, certified finalize. Neighbour SETS must equal the oracle's on
+    every non-tie row - including clouds that are not a multiple of the 64-candidate / 256-query tiles and kk up to
+    the 32 the merged class list supports."""
+    B, C = 2, 64
+    assert lib.fs_knn_feat_tc_supported(B, N, C, k, int(self_loop)) == 1
+    gen = torch.Generator().manual_seed(N * 3 + k)
+    feat = torch.randn(B, C, N, generator=gen)
+    feat = torch.nn.functional.leaky_relu(feat + 0.5 * torch.randn(B, C, 1, generator=gen), 0.2)   # post-activation-like
+    pm = ops.to_point_major(feat.to(DEV)).contiguous()
+    idx = ops.knn_features(pm, B, N, k, self_loop=self_loop)
+    assert idx.shape == (B, N, k) and int(idx.min()) >= 0 and int(idx.max()) < N
+    rep = compare_knn(idx, None, feat, k, self_loop, O.knn_with_gap)
+    assert rep["mismatch_non_tie_rows"] == 0, rep
+    # same result as the exact SIMT kernel (which also returns the distances)
+    idx_exact, _ = ops.knn_features(pm, B, N, k, self_loop=self_loop, return_dist=True)
+    same = (idx.sort(-1)[0] == idx_exact.sort(-1)[0]).all(-1)
+    assert int((~same).sum()) <= rep["tie_rows"], (int((~same).sum()), rep)
+
+
 def test_knn_degenerate_inputs(lib):
     # all points identical (thesis/utils.py:22-23 forwards an all-zero cloud): must not hang or go out of bounds
     z = torch.zeros(1, 3, 128, device=DEV)
