@@ -46,15 +46,23 @@ __device__ __forceinline__ void fs_unpack_key(unsigned long long key, float& d, 
     d = __uint_as_float(o ^ ((o & 0x80000000u) ? 0x80000000u : 0xffffffffu));
     i = (int)(uint32_t)key;
 }
-// Ascending bitonic sort of 32*H keys, element e = h*32 + lane (H = 1 or 2).
+// Ascending bitonic sort of 32*H keys, element e = h*32 + lane (H = 1, 2 or 4).
 template <int H>
 __device__ __forceinline__ void fs_warp_bitonic_sort_keys(unsigned long long (&key)[H], int lane) {
 #pragma unroll
     for (int k = 2; k <= 32 * H; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j == 32) {                       // H == 2, final merge: partner is the lane's other element
-                if (key[H - 1] < key[0]) { const unsigned long long t = key[0]; key[0] = key[H - 1]; key[H - 1] = t; }
+            if (j >= 32) {                       // partner element lives in the same lane: slot h ^ (j / 32)
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const int hp = h | (j >> 5);
+                    if ((h & (j >> 5)) == 0 && hp < H) {
+                        const bool up = ((h * 32) & k) == 0 || k == 32 * H;      // lane bits do not reach k here
+                        const bool swap = up ? key[hp] < key[h] : key[h] < key[hp];
+                        if (swap) { const unsigned long long t = key[h]; key[h] = key[hp]; key[hp] = t; }
+                    }
+                }
             } else {
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
@@ -68,6 +76,21 @@ __device__ __forceinline__ void fs_warp_bitonic_sort_keys(unsigned long long (&k
             }
         }
     }
+}
+
+// Ascending bitonic sort of one float per lane (values only).
+__device__ __forceinline__ float fs_warp_bitonic_sort_f(float v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const float o = __shfl_xor_sync(FS_FULL_MASK, v, j);
+            const bool up = (lane & k) == 0 || k == 32;
+            const bool lower = (lane & j) == 0;
+            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
+        }
+    }
+    return v;
 }
 
 template <int KPL>
