@@ -3,8 +3,6 @@
 // summed without FMA contraction, the dot product is an FMA chain, and the expansion is evaluated
 // as (xx_i - 2*dot) + xx_j with the diagonal forced to 0.
 #include "warp_select.cuh"
-#include <stdlib.h>
-#include <string.h>
 
 namespace {
 
@@ -240,203 +238,6 @@ knn3d_regs_kernel(const float* __restrict__ coords, long long batch_stride, long
 }
 
 // ---------------------------------------------------------------------------------------------
-// Batched 3-D kNN with block pruning, for clouds whose rows are spatially ordered (DGCNNBase sorts every cloud along
-// the Morton curve): 32 consecutive points form a compact block with a small bounding box.
-//   boxes   : every CTA computes the AABB of each 32-point block of its cloud (shared memory, 64 boxes);
-//   seed    : the query's own block and its two neighbours give 3 distances per lane; tau = kk-th smallest of the
-//             32 lane minima (kk distinct candidates lie at or below it, so it bounds the kk-th smallest distance);
-//   prune   : a block is skipped when its box is further from the query than tau plus a margin that covers the
-//             rounding of the reference's expansion (xx_i - 2 x.y) + xx_j: every candidate in a skipped block has a
-//             COMPUTED distance strictly above tau, hence cannot be among the kk smallest;
-//   collect : the surviving blocks (about a quarter of the cloud) are evaluated with the same arithmetic as the
-//             other kernels, candidates <= tau are compacted with ballots and ordered by a bitonic network on
-//             packed (distance, index) keys - the same total order, hence the same result.
-// Degenerate queries (fewer than kk finite distances, more than CAP candidates at or below tau: duplicate points,
-// NaN / Inf coordinates) stream every candidate through the warp-select like knn3d_regs_kernel does.
-// ---------------------------------------------------------------------------------------------
-constexpr int KNN3P_WARPS = 8;
-constexpr int KNN3P_THREADS = KNN3P_WARPS * 32;
-constexpr int KNN3P_QPW = 8;                                  // queries per warp (sequential)
-constexpr int KNN3P_TILE_Q = KNN3P_WARPS * KNN3P_QPW;
-constexpr int KNN3P_MAXBLK = 64;                              // N <= 2048
-constexpr int KNN3P_CAP = 128;                                // survivor slots per warp
-
-__global__ void __launch_bounds__(KNN3P_THREADS)
-knn3d_pruned_kernel(const float* __restrict__ coords, long long batch_stride, long long chan_stride,
-                    long long point_stride, int N, int k, int self_loop, int diag_zero,
-                    int32_t* __restrict__ idx, float* __restrict__ dist2) {
-    extern __shared__ float smem[];
-    const int nblk = (N + 31) >> 5;
-    const int chunk = nblk * 32;
-    float4* sp = reinterpret_cast<float4*>(smem);                                  // [chunk] (x, y, z, |p|^2)
-    float4* blo = sp + chunk;                                                      // [64] box minima
-    float4* bhi = blo + KNN3P_MAXBLK;                                              // [64] box maxima
-    float* qd_all = reinterpret_cast<float*>(bhi + KNN3P_MAXBLK);                  // [warps][64] warp-select queue
-    int* qi_all = reinterpret_cast<int*>(qd_all + KNN3P_WARPS * 64);
-    unsigned long long* hk_all = reinterpret_cast<unsigned long long*>(qi_all + KNN3P_WARPS * 64);   // [warps][CAP]
-    __shared__ int s_pmax_bits;
-
-    const int b = blockIdx.y;
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const float* cb = coords + (long long)b * batch_stride;
-    const int kk = k + (self_loop ? 0 : 1);
-    const int skip = self_loop ? 0 : 1;
-
-    if (threadIdx.x == 0) s_pmax_bits = 0;
-    for (int j = threadIdx.x; j < chunk; j += KNN3P_THREADS) {
-        float4 p = make_float4(0.f, 0.f, 0.f, INFINITY);      // padding beyond the cloud: distance +inf
-        if (j < N) {
-            const long long o = (long long)j * point_stride;
-            p.x = __ldg(cb + o); p.y = __ldg(cb + chan_stride + o); p.z = __ldg(cb + 2 * chan_stride + o);
-            p.w = sqnorm3(p.x, p.y, p.z);
-        }
-        sp[j] = p;
-    }
-    __syncthreads();
-    // bounding boxes and the largest squared norm of the cloud
-    float wmax = 0.f;
-    for (int blk = warp; blk < nblk; blk += KNN3P_WARPS) {
-        const int j = blk * 32 + lane;
-        const float4 p = sp[j];
-        const bool in = j < N;
-        float lx = in ? p.x : INFINITY, ly = in ? p.y : INFINITY, lz = in ? p.z : INFINITY;
-        float hx = in ? p.x : -INFINITY, hy = in ? p.y : -INFINITY, hz = in ? p.z : -INFINITY;
-        float nm = in ? p.w : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lx = fminf(lx, __shfl_xor_sync(FS_FULL_MASK, lx, o)); ly = fminf(ly, __shfl_xor_sync(FS_FULL_MASK, ly, o));
-            lz = fminf(lz, __shfl_xor_sync(FS_FULL_MASK, lz, o));
-            hx = fmaxf(hx, __shfl_xor_sync(FS_FULL_MASK, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(FS_FULL_MASK, hy, o));
-            hz = fmaxf(hz, __shfl_xor_sync(FS_FULL_MASK, hz, o));
-            nm = fmaxf(nm, __shfl_xor_sync(FS_FULL_MASK, nm, o));
-        }
-        if (lane == 0) { blo[blk] = make_float4(lx, ly, lz, 0.f); bhi[blk] = make_float4(hx, hy, hz, 0.f); }
-        wmax = fmaxf(wmax, nm);
-    }
-    if (lane == 0 && wmax == wmax) atomicMax(&s_pmax_bits, __float_as_int(wmax));   // non-negative floats order as ints
-    __syncthreads();
-    const float pmax = __int_as_float(s_pmax_bits);
-
-    unsigned long long* hk = hk_all + warp * KNN3P_CAP;
-    FsWarpSelect<1> sel;
-
-    auto dist_to = [&](const float4& p, float qx, float qy, float qz, float qq) {
-        const float dot = fmaf(qz, p.z, fmaf(qy, p.y, __fmul_rn(qx, p.x)));
-        return diag_zero ? __fadd_rn(__fsub_rn(qq, 2.0f * dot), p.w) : __fadd_rn(__fsub_rn(p.w, 2.0f * dot), qq);
-    };
-
-    for (int r = 0; r < KNN3P_QPW; ++r) {
-        const int q = blockIdx.x * KNN3P_TILE_Q + r * KNN3P_WARPS + warp;
-        if (q >= N) break;                                    // warp-uniform
-        const float4 qp = sp[q];
-        const float qx = qp.x, qy = qp.y, qz = qp.z, qq = qp.w;
-        const long long row = ((long long)b * N + q) * k;
-
-        // ---- seed: own block and its neighbours -> tau -------------------------------------------------------
-        const int b0 = q >> 5;
-        const int s0 = min(max(b0 - 1, 0), nblk - 3);
-        float m = INFINITY;
-#pragma unroll
-        for (int sb = 0; sb < 3; ++sb) {
-            const int j = (s0 + sb) * 32 + lane;
-            float d = dist_to(sp[j], qx, qy, qz, qq);
-            if (diag_zero && j == q) d = 0.f;                 // general_utils.py:52
-            m = fminf(m, d);                                  // NaN distances are ignored
-        }
-        if (!(m == m)) m = INFINITY;
-        const float tau = __shfl_sync(FS_FULL_MASK, fs_warp_bitonic_sort_f(m, lane), kk - 1);
-
-        bool streamed = !(tau < INFINITY);
-        int cnt = 0;
-        if (!streamed) {
-            // ---- prune: box lower bounds against tau (+ rounding margin of the expansion form) ----------------
-            const float bound = fmaf(tau, 1.0e-5f, tau) + 4.0e-6f * (qq + pmax) + 1e-30f;
-            unsigned mask[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int blk = h * 32 + lane;
-                float lb = INFINITY;
-                if (blk < nblk) {
-                    const float4 lo = blo[blk], hi = bhi[blk];
-                    const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.f);
-                    const float dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.f);
-                    const float dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.f);
-                    lb = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                }
-                mask[h] = __ballot_sync(FS_FULL_MASK, lb <= bound);      // NaN boxes (lb != lb) are kept out: such rows stream
-            }
-            // ---- collect the candidates at or below tau from the surviving blocks -----------------------------
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                unsigned todo = mask[h];
-                while (todo) {
-                    const int blk = h * 32 + __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int j = blk * 32 + lane;
-                    float d = dist_to(sp[j], qx, qy, qz, qq);
-                    if (diag_zero && j == q) d = 0.f;
-                    const bool hit = d <= tau;                // padding rows carry +inf
-                    const unsigned hm = __ballot_sync(FS_FULL_MASK, hit);
-                    const int pos = cnt + __popc(hm & ((1u << lane) - 1u));
-                    if (hit && pos < KNN3P_CAP) hk[pos] = fs_pack_key(d, j);
-                    cnt += __popc(hm);
-                }
-            }
-            __syncwarp();
-            if (cnt < kk || cnt > KNN3P_CAP) streamed = true;
-        }
-        if (!streamed) {
-            const unsigned long long pad = fs_pack_key(INFINITY, FS_IDX_PAD);
-            if (cnt <= 32) {
-                unsigned long long key[1] = {lane < cnt ? hk[lane] : pad};
-                fs_warp_bitonic_sort_keys<1>(key, lane);
-                if (lane >= skip && lane < kk) {
-                    float d; int i;
-                    fs_unpack_key(key[0], d, i);
-                    idx[row + lane - skip] = i;
-                    if (dist2) dist2[row + lane - skip] = d;
-                }
-            } else if (cnt <= 64) {
-                unsigned long long key[2] = {hk[lane], lane + 32 < cnt ? hk[lane + 32] : pad};
-                fs_warp_bitonic_sort_keys<2>(key, lane);
-                if (lane >= skip && lane < kk) {              // kk <= 32: the answer sits in slot 0
-                    float d; int i;
-                    fs_unpack_key(key[0], d, i);
-                    idx[row + lane - skip] = i;
-                    if (dist2) dist2[row + lane - skip] = d;
-                }
-            } else {
-                unsigned long long key[4];
-#pragma unroll
-                for (int h = 0; h < 4; ++h) key[h] = h * 32 + lane < cnt ? hk[h * 32 + lane] : pad;
-                fs_warp_bitonic_sort_keys<4>(key, lane);
-                if (lane >= skip && lane < kk) {
-                    float d; int i;
-                    fs_unpack_key(key[0], d, i);
-                    idx[row + lane - skip] = i;
-                    if (dist2) dist2[row + lane - skip] = d;
-                }
-            }
-            __syncwarp();
-            continue;
-        }
-        // ---- degenerate query: stream every candidate through the warp-select ---------------------------------
-        sel.init(qd_all + warp * 64, qi_all + warp * 64, kk);
-#pragma unroll 1
-        for (int blk = 0; blk < nblk; ++blk) {
-            const int j = blk * 32 + lane;
-            float d = dist_to(sp[j], qx, qy, qz, qq);
-            if (diag_zero && j == q) d = 0.f;
-            sel.offer(d, j, j < N);
-        }
-        sel.finish();
-        sel.store(skip, idx + row, dist2 ? dist2 + row : nullptr, 0, 0, INFINITY);
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Offset-segmented kNN (pointops knnquery): one warp per query, candidates read through L1.
 // ---------------------------------------------------------------------------------------------
 template <int KPL>
@@ -590,12 +391,6 @@ knn_feat_kernel(const float* __restrict__ x, int ldx, int N, int C, int k, int s
     }
 }
 
-// FS_KNN3D=pruned selects the block-pruned 3-D kernel (read per call; default: register-resident kernel).
-bool knn3d_pruned_enabled() {
-    const char* e = getenv("FS_KNN3D");
-    return e && strcmp(e, "pruned") == 0;
-}
-
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) {
@@ -617,18 +412,6 @@ extern "C" int fs_knn3d(int device, fs_stream_t stream_, const float* coords, lo
     if (kk > N || kk > FS_MAX_K + 1) return FS_ERR_BAD_ARG;
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (N <= 2048 && N >= 96 && kk <= 32 && knn3d_pruned_enabled()) {
-        // block-pruned variant for spatially ordered clouds
-        const int nblk = (N + 31) / 32;
-        const size_t ps = (size_t)nblk * 32 * 16 + 2 * KNN3P_MAXBLK * 16 + KNN3P_WARPS * 64 * 8 +
-                          (size_t)KNN3P_WARPS * KNN3P_CAP * 8;
-        int e = set_smem(knn3d_pruned_kernel, ps);
-        if (e) return e;
-        knn3d_pruned_kernel<<<dim3(fs_div_up(N, KNN3P_TILE_Q), B), KNN3P_THREADS, ps, stream>>>(
-            coords, batch_stride, chan_stride, point_stride, N, k, self_loop, diag_zero, idx, dist2);
-        FS_RETURN_IF_LAUNCH_FAILED();
-        return FS_OK;
-    }
     if (N <= 2048 && kk <= 64) {
         // register-resident variant: every lane keeps its N/32 distances
         dim3 rgrid(fs_div_up(N, KNN3R_TILE_Q), B);

@@ -78,21 +78,6 @@ __device__ __forceinline__ void fs_warp_bitonic_sort_keys(unsigned long long (&k
     }
 }
 
-// Ascending bitonic sort of one float per lane (values only).
-__device__ __forceinline__ float fs_warp_bitonic_sort_f(float v, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const float o = __shfl_xor_sync(FS_FULL_MASK, v, j);
-            const bool up = (lane & k) == 0 || k == 32;
-            const bool lower = (lane & j) == 0;
-            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
-        }
-    }
-    return v;
-}
-
 template <int KPL>
 struct FsWarpSelect {
     static_assert(KPL == 1 || KPL == 2 || KPL == 4, "list length must be 32, 64 or 128");

@@ -9,7 +9,4 @@ timeout 60 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/be
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu.log 2>&1
 timeout 90 ncu --set full --clock-control none --import-source on -k regex:edgeconv_gather_smem -s 1 -c 1 -o gpurun_out/full_gather -f python tools/run_gather.py > gpurun_out/ncu_gather.log 2>&1
 timeout 90 ncu --set full --clock-control none --import-source on -k regex:'knn_tc_select|knn_tc_finalize' -s 4 -c 2 -o gpurun_out/full_tc -f python tools/run_knn_tc.py > gpurun_out/ncu_tc.log 2>&1
-# experimental (off by default): block-pruned 3-D kNN
-FS_KNN3D=pruned timeout 90 python -m pytest tests -m gpu -q > gpurun_out/pytest_pruned.log 2>&1; echo "pytest(pruned) rc=$?" >> gpurun_out/pytest_pruned.log; tail -2 gpurun_out/pytest_pruned.log
-timeout 60 python tools/microbench.py knn3d > gpurun_out/mb_knn3d.log 2>&1; cat gpurun_out/mb_knn3d.log
 ls -la gpurun_out | tail -12

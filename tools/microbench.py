@@ -27,20 +27,7 @@ xpm = x.transpose(1, 2).reshape(B * N, 3).contiguous()
 W = torch.randn(3, 64, device=dev)
 feat = torch.nn.functional.leaky_relu(torch.sin(xpm @ W * 3) + 0.3, 0.2).contiguous()
 
-timeit(lambda: ops.knn_coords(x, k, self_loop=True), label='knn_coords (3-D) [FS_KNN3D=%s]' % os.environ.get('FS_KNN3D', 'regs'))
-if len(sys.argv) > 1 and sys.argv[1] == 'knn3d':
-    os.environ['FS_KNN3D'] = 'pruned'
-    a = ops.knn_coords(x, k, self_loop=True)
-    timeit(lambda: ops.knn_coords(x, k, self_loop=True), label='knn_coords (3-D) [pruned, Morton-sorted]')
-    os.environ.pop('FS_KNN3D')
-    b = ops.knn_coords(x, k, self_loop=True)
-    print('pruned == regs (sorted sets):', torch.equal(a.sort(-1)[0], b.sort(-1)[0]), 'ordered:', torch.equal(a, b))
-    xs = x[:, :, torch.randperm(N, device=dev)]
-    os.environ['FS_KNN3D'] = 'pruned'
-    timeit(lambda: ops.knn_coords(xs, k, self_loop=True), label='knn_coords (3-D) [pruned, shuffled cloud]')
-    os.environ.pop('FS_KNN3D')
-    timeit(lambda: ops.knn_coords(xs, k, self_loop=True), label='knn_coords (3-D) [regs, shuffled cloud]')
-    sys.exit(0)
+timeit(lambda: ops.knn_coords(x, k, self_loop=True), label='knn_coords (3-D)')
 timeit(lambda: ops.knn_features(feat, B, N, k, self_loop=True), label='knn_features (tc path)')
 _lib.time_calls.clear()
 
