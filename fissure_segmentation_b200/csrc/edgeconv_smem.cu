@@ -9,9 +9,10 @@
 // rate), HBM traffic drops to the compulsory bytes (table once, idx once per slice via L2, outputs once).
 //
 // Thread mapping: LPR = CS/4 lanes per point (each lane owns 4 channels = one float4 per neighbour row),
-// 32/LPR points per warp. The indices, b_i row and in-degree of the NEXT point are prefetched into registers
-// while the current one is reduced. Batch statistics: same shifted fp64 per-point formula as
-// edgeconv_gather_kernel (edgeconv.cu), committed through fs_stats_commit.
+// 32/LPR points per warp. The slice is stored as KEYS (sign bit flipped on channels that take the minimum), so the
+// loop is a pure arg-max. The indices, b_i rows and in-degrees of a warp's NEXT 32/LPR points are staged by
+// cp.async into a per-warp double buffer while the current ones are reduced. Batch statistics: same shifted fp64
+// per-point formula as edgeconv_gather_kernel (edgeconv.cu), committed through fs_stats_commit.
 #include "fs_common.cuh"
 #include "edgeconv_smem.cuh"
 

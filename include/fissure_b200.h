@@ -77,12 +77,16 @@ int fs_knn_feat(int device, fs_stream_t stream, const float* x, int ldx, int B, 
 
 /*
  * Same contract as fs_knn_feat for C == 64 features, on the 5th-generation tensor cores: the
- * -2 X X^T contraction runs as tcgen05.mma on TMA-staged bf16 hi/lo-split tiles (accumulators in TMEM),
- * the epilogue keeps 32 candidates per query, and an exact FP32 re-rank (identical arithmetic to
- * fs_knn_feat) selects the k nearest. Rows whose candidate set cannot be certified complete are
- * recomputed by the exact kernel, so the result equals fs_knn_feat's.
+ * -2 X X^T contraction runs as tcgen05.mma on TMA-staged bf16 hi/lo-split tiles (accumulators in TMEM).
+ * Two sweeps over the candidates: the first keeps 64 class minima per query and derives an upper bound of
+ * the k-th distance, the second lists every candidate below it (about 1.2 k per query); entries the
+ * approximation cannot decide are re-evaluated in fs_knn_feat's exact FP32 arithmetic. Rows whose candidate
+ * set cannot be certified complete (list overflow, NaN) are recomputed by the exact kernel, so the neighbour
+ * SET equals fs_knn_feat's; the order inside the set follows the approximate distances. dist2 != NULL
+ * selects the exact kernel for every row.
  *   workspace        >= fs_knn_feat_tc_workspace_bytes(B, N, C, k) bytes, 256-byte aligned
- * fs_knn_feat_tc_supported returns 1 when the shape is handled (C == 64, k + 5 <= 32, N <= 8192).
+ * fs_knn_feat_tc_supported returns 1 when the shape is handled by the tensor-core kernels
+ * (C == 64, k + !self_loop <= 32, 64 <= N <= 32768); other shapes run the exact kernel.
  */
 size_t fs_knn_feat_tc_workspace_bytes(int B, int N, int C, int k);
 int fs_knn_feat_tc_supported(int B, int N, int C, int k, int self_loop);
