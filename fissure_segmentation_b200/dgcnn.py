@@ -183,7 +183,7 @@ class EdgeConv(nn.Module):
             h = ops.edge_first3(x_pm.float().contiguous(), first.conv.weight, first.norm, graph, cdt)
             return self._finish_multilayer(h, graph)
         w = first.weight_matrix()
-        w_cat = torch.cat([w[:, :C], w[:, C:] - w[:, :C]], dim=0)             # [W1 ; W2 - W1]  (2Cp, C)
+        w_cat = ops.edge_weight_table(w, C)                                    # [W1 ; W2 - W1]  (2Cp, C)
         # The per-point table stays fp32 in every precision mode: y = a_j + b_i = W1 (x_j - x_i) + W2 x_i
         # cancels the common part of a_j and -b_i, so rounding a to 16 bits would wipe out the local
         # differences the layer is about (measured: cosine 0.998 on gradients with bf16 tables).

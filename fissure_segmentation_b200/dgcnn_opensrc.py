@@ -48,7 +48,7 @@ def edgeconv_stage(x_pm, B, N, k, conv, graph, cdt):
             graph = KnnGraph(idx)
     C = x_pm.shape[1]
     w = conv2d.weight.view(conv2d.out_channels, 2 * C)
-    w_cat = torch.cat([w[:, :C], w[:, C:] - w[:, :C]], dim=0)
+    w_cat = ops.edge_weight_table(w, C)
     table = ops.table_gemm(x_pm.float().contiguous(), w_cat.float())   # fp32 table in every mode (see dgcnn.EdgeConv.forward_pm)
     return ops.edgeconv_fused(table, bn.weight, bn.bias, graph, bn.running_mean, bn.running_var,
                               bn.num_batches_tracked, bn.training, eps=bn.eps, momentum=bn.momentum)

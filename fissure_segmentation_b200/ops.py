@@ -296,7 +296,8 @@ class _EdgeReduceFn(torch.autograd.Function):
         stats = _stats_buffer(Cp, dev) if training else None
         _lib.call("fs_edge_reduce", z, z, _lib.dtype_code(z), P, k, Cp, gamma32, sel, arg, None, stats)
         coef = _bn_coef(z, stats, P * k, gamma32, beta32, running_mean, running_var, nbt, training, Cp, eps, momentum)
-        out = torch.empty(P, Cp, dtype=z.dtype, device=dev)
+        # fp32 output in every precision mode: it is the next layer's kNN / table input (no bf16 round trip, no cast)
+        out = torch.empty(P, Cp, dtype=torch.float32, device=dev)
         _lib.call("fs_edgeconv_apply", z, sel, None, 0, 0, P, Cp, coef, out, _lib.dtype_code(out), out.stride(0))
         ctx.k = k
         ctx.training = training
@@ -498,6 +499,38 @@ class _TableGemmFn(torch.autograd.Function):
 
 def table_gemm(x, w):
     return _TableGemmFn.apply(x, w)
+
+
+class _EdgeWeightFn(torch.autograd.Function):
+    """[W1 ; W2 - W1] (2Cp, C) from the EdgeConv weight W = [W1 | W2] (Cp, 2C) (models/dgcnn.py:36 column order).
+    Written as `cat([w[:, :C], w[:, C:] - w[:, :C]])` autograd replays slices, a subtraction and a concatenation:
+    4 small kernels forward and 9 backward per layer; here it is 2 + 2."""
+
+    @staticmethod
+    def forward(ctx, w, C):
+        Cp = w.shape[0]
+        wf = w if w.dtype == torch.float32 else w.float()
+        out = torch.empty(2 * Cp, C, dtype=torch.float32, device=w.device)
+        out[:Cp].copy_(wf[:, :C])
+        torch.sub(wf[:, C:], wf[:, :C], out=out[Cp:])
+        ctx.C = C
+        ctx.w_dtype = w.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        C = ctx.C
+        Cp = g.shape[0] // 2
+        g = g.float()
+        dw = torch.empty(Cp, 2 * C, dtype=torch.float32, device=g.device)
+        torch.sub(g[:Cp], g[Cp:], out=dw[:, :C])        # dW1 = g_a - g_b
+        dw[:, C:].copy_(g[Cp:])                         # dW2 = g_b
+        return dw.to(ctx.w_dtype), None
+
+
+def edge_weight_table(w, C):
+    """w (Cp, 2C) -> fp32 (2Cp, C) = [W1 ; W2 - W1], the right-hand side of the per-point table GEMM."""
+    return _EdgeWeightFn.apply(w, C)
 
 
 # ------------------------------------------------------------------------------------------- first layer, 3-D input
