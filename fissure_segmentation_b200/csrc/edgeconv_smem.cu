@@ -296,11 +296,9 @@ int launch(cudaStream_t stream, const float* table, int ld, const int32_t* idx, 
     int table_bytes;
     const size_t smem = gs_smem_bytes(N, k, CS, &table_bytes);
     auto kern = edgeconv_gather_smem_kernel<CS, NCHUNK, MODE, OT>;
-    static bool configured = false;      // idempotent attribute; a race only repeats the call
-    if (!configured) {
+    {   // per launch: the attribute is per device and the caller may use several devices from one process
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM_CAP);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
     }
     const int slices = CP / CS;
     int split = 1;                       // small batches: several CTAs share a slice (each stages it again from L2)
