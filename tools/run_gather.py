@@ -1,5 +1,5 @@
 """Three launches of the train-mode EdgeConv gather at the bench shape (target of the ncu --set full capture)."""
-import os, sys, torch
+import sys, torch
 sys.path.insert(0, '.')
 from fissure_segmentation_b200 import ops, synth, _lib
 B, N, k, Cp = 32, 2048, 20, 64
