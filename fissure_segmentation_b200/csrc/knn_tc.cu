@@ -8,19 +8,21 @@
 //                 operand tables A', B' (P x 256 bf16) such that one K = 208 tensor-core product gives
 //                     A'_i . B'_j = |x_i|^2 + |x_j|^2 - 2 x_i.x_j        (error ~ 2^-15 (|x_i|^2+|x_j|^2))
 //                 (hi*hi + lo*hi + hi*lo in K = 192; the squared norms ride in 16 extra K columns).
-//   2. select   : one CTA per (cloud, 256 queries). TMA stages 128B-swizzled operand tiles, one elected
-//                 thread issues tcgen05.mma (M = 128 queries x N = 64 candidates, two query tiles share
-//                 every candidate tile) into double-buffered TMEM accumulators, four epilogue warps read
-//                 the scores with tcgen05.ld, one query row per TMEM lane. The distance matrix is swept
-//                 twice: sweep 1 keeps, per row, the minimum of each of 32 interleaved column classes
-//                 (32 FMNMX per 32 scores) — the kk-th smallest class minimum is an upper bound tau of the
-//                 kk-th smallest distance; sweep 2 stores every (index, distance) with distance <= tau +
-//                 2 err (about 1.5 kk entries per row). No sorted list, no dependent chains: MMA-bound.
-//   3. finalize : one warp per query sorts its <= 64 survivors by approximate distance. Entries further
-//                 than 2 err from the kk-th are decided by the approximation alone; the few within 2 err
-//                 are re-evaluated exactly in the reference's FP32 arithmetic (same code as knn.cu), so
-//                 the neighbour SET equals the exact kernel's. Rows whose survivor list overflowed are
-//                 recomputed by the exact SIMT kernel.
+//   2. select   : one CTA per (cloud, 256 queries). TMA stages 128B-swizzled candidate tiles (5 stages), one
+//                 thread chosen with elect.sync issues tcgen05.mma (M = 128 queries x N = 64 candidates, the
+//                 query operand of both query tiles lives in TMEM) into double-buffered TMEM accumulators;
+//                 16 epilogue warps read the scores with tcgen05.ld, one query row per TMEM lane and one warp per
+//                 32-column half of the tile. The distance matrix is swept twice: sweep 1 keeps, per thread, the
+//                 minimum of each of 32 interleaved column classes (one FMNMX per score) - 64 disjoint classes
+//                 per row; the kk-th smallest class minimum is an upper bound tau of the kk-th smallest
+//                 distance. Sweep 2 lists every (index, distance) with distance <= tau + 2 err (about 1.2 kk
+//                 entries per row) in two per-half survivor lists.
+//   3. finalize : one warp per query sorts its survivors (packed 64-bit keys, bitonic network) by approximate
+//                 distance. Entries further than 2 err from the kk-th are decided by the approximation alone;
+//                 the few within 2 err are re-evaluated exactly in the reference's FP32 arithmetic (same code
+//                 as knn.cu), so the neighbour SET equals the exact kernel's. Rows whose survivor lists
+//                 overflowed are recomputed by the exact SIMT kernel.
+// What bounds the select kernel and what was tried is recorded in DESIGN.md section 4.
 #include <cuda.h>
 
 #include "warp_select.cuh"
