@@ -157,3 +157,22 @@ def test_statistics_arena_is_zero_filled_and_grows():
     assert e.data_ptr() != ar.buf.data_ptr() and float(e.abs().max()) == 0.0
     ar.begin_step(dev)
     assert ar.cap == 18 and float(ar.buf.abs().max()) == 0.0
+
+
+def test_tensor_core_knn_host_contract(lib):
+    """Host-side entry points of the tcgen05 kNN that need no device: the supported shape range documented in
+    include/fissure_b200.h and the workspace size (two bf16 operand tables of 256 columns, two 128-slot survivor lists,
+    two counts per row, norms; every block 256-byte aligned)."""
+    ok = lib.fs_knn_feat_tc_supported
+    assert ok(32, 2048, 64, 20, 1) == 1 and ok(32, 2048, 64, 20, 0) == 1
+    assert ok(2, 64, 64, 5, 1) == 1 and ok(2, 63, 64, 5, 1) == 0                    # N >= 64
+    assert ok(2, 2048, 64, 32, 1) == 1 and ok(2, 2048, 64, 32, 0) == 0              # k + !self_loop <= 32
+    assert ok(2, 2048, 128, 20, 1) == 0 and ok(2, 2048, 9, 20, 1) == 0              # C == 64 only
+    assert ok(1, 32768, 64, 20, 1) == 1 and ok(1, 32769, 64, 20, 1) == 0
+    ws = lib.fs_knn_feat_tc_workspace_bytes
+    P = 32 * 2048
+    need = 2 * P * 256 * 2 + 2 * P * 128 * 4 + P * 4 * 2 + 2 * P * 4 + P
+    got = ws(32, 2048, 64, 20)
+    assert need <= got <= need + 16 * 256 + 32 * 64 * 4 + 32 * 8                    # payload + alignment slack + per-cloud blocks
+    assert ws(64, 2048, 64, 20) > got and ws(32, 2048, 64, 20) == got               # monotone, deterministic
+    assert ws(1, 64, 64, 5) % 256 == 0
