@@ -176,3 +176,22 @@ def test_tensor_core_knn_host_contract(lib):
     assert need <= got <= need + 16 * 256 + 32 * 64 * 4 + 32 * 8                    # payload + alignment slack + per-cloud blocks
     assert ws(64, 2048, 64, 20) > got and ws(32, 2048, 64, 20) == got               # monotone, deterministic
     assert ws(1, 64, 64, 5) % 256 == 0
+
+
+def test_built_library_contains_blackwell_instructions(lib):
+    """SASS evidence (no GPU needed): the tensor-core kNN really issues tcgen05.mma with TMA-staged operands and
+    TMEM loads/stores, and the shared-memory gather stages its indices with cp.async - the mnemonics listed in the
+    B200 profiling recipe (tcgen05.mma -> UTCHMMA, cp.async.bulk.tensor -> UTMALDG, tcgen05.ld/st -> LDTM/STTM,
+    cp.async -> LDGSTS). sm_100a only: no other architecture is embedded."""
+    import shutil
+    import subprocess
+    from fissure_segmentation_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR", "LDGSTS", "SYNCS"):
+        assert mnemonic in sass, mnemonic
+    assert sass.count("UTCHMMA") == 26                       # 13 K steps x 2 query tiles, straight-line issue
+    archs = set(line.split("=")[1].strip() for line in sass.splitlines() if line.strip().startswith("arch ="))
+    assert archs == {"sm_100a"}, archs
