@@ -5,7 +5,8 @@
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
         --master-port 29500 bench.py --gpus 8 --steps 20 --warmup 5
-    python bench.py --impl reference --steps 5 --warmup 2      # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps 5 --warmup 2      # the reference's own CPU path
+    python bench.py --workload configC | static40 | chamfer | pointtransformer | inference   # BASELINE configs[2..4], f4
 
 Prints ONE JSON line (rank 0). See DESIGN.md section "Measurement" for the definitions.
 """
@@ -28,35 +29,37 @@ import torch.nn.functional as F  # noqa: E402
 
 METRIC = "point clouds/sec DGCNNSeg fwd+bwd N=2048 k=20"
 UNIT = "clouds/s"
-GATHER_DRAM_BYTES = 41_340_416      # ncu --set full, one launch, B=32 N=2048 k=20 (profiles/r01_g_gather_smem_full.txt)
-
-
-def _tensor_peak():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            return float(json.load(f).get("bf16_tflops", 1626.3))
-    return 1626.3
-
-
-TENSOR_PEAK_TFLOPS = _tensor_peak()
+NCU_METRICS = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")     # written by tools/ncu_metrics.py from a capture
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="clouds per GPU")
-    ap.add_argument("--points", type=int, default=2048)
-    ap.add_argument("--k", type=int, default=20)
+    ap.add_argument("--workload", default="train",
+                    choices=["train", "configC", "static40", "chamfer", "pointtransformer", "inference"])
+    ap.add_argument("--batch", type=int, default=None, help="clouds per GPU (default: per workload)")
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--static", action="store_true", help="static coordinate graph (train.py --static)")
-    ap.add_argument("--cpu-batch", type=int, default=2, help="clouds per CPU-baseline step")
+    ap.add_argument("--cpu-batch", type=int, default=None, help="clouds per CPU step (default: 8 for cpu_baseline, "
+                    "the GPU batch for --impl reference when the host has the memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
-    return ap.parse_args()
+    args = ap.parse_args()
+    wl = {"train": (32, 2048, 20, 3), "configC": (8, 8192, 40, 9), "static40": (32, 2048, 40, 3),
+          "chamfer": (64, 2048, 0, 3), "pointtransformer": (4, 4096, 16, 3), "inference": (1, 20000, 20, 3)}[args.workload]
+    args.batch = args.batch or wl[0]
+    args.points = args.points or wl[1]
+    args.k = args.k or wl[2]
+    args.in_features = wl[3]
+    if args.workload in ("configC", "static40"):
+        args.static = True          # the configuration the authors trained with k = 40 (bash_scripts/redo_dgcnn_seg.sh:6-8)
+    return args
 
 
 def peaks():
@@ -64,8 +67,25 @@ def peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops", 1590.0)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def from_profile(kernel_substr):
+    """Counter values of one kernel from the committed ncu capture of this round (profiles/r02_ncu_metrics.json,
+    written by tools/ncu_metrics.py with the capture's file name and git revision). None when no capture exists: the
+    bench line never carries a hand-copied constant."""
+    if not os.path.exists(NCU_METRICS):
+        return None
+    with open(NCU_METRICS) as f:
+        data = json.load(f)
+    for name, rec in data.get("kernels", {}).items():
+        if kernel_substr in name:
+            out = dict(rec)
+            out["kernel"] = name
+            out["source"] = {"file": os.path.relpath(NCU_METRICS, ROOT), "git": data.get("git"), "capture": data.get("capture")}
+            return out
+    return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -112,52 +132,97 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle's restatement of the reference's PyTorch CPU path
+# the reference itself (baseline/_ref or /root/reference through oracle/reference_shim.py), else the oracle port
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps(args, steps, warmup, max_seconds=120.0):
-    """DGCNNSeg forward + CE + backward + Adam on the host cores, `cpu_batch` clouds per step, fp32,
-    autocast off (model_trainer.py:76 disables it on CPU). Returns (clouds/s, s/step, threads, n_steps)."""
-    from fissure_segmentation_b200 import synth
-    from oracle import dgcnn_oracle as O
+def build_reference_model(args, device):
+    """(step_fn(x, y) -> loss, kind): the UNMODIFIED reference DGCNNSeg with Adam + cross-entropy exactly as
+    model_trainer.py:57, 154-195 drives it; falls back to the pinned oracle port when the staged files are absent."""
+    from oracle import reference_shim
     torch.manual_seed(0)
-    B = args.cpu_batch
-    x, y = synth.make_batch(B, args.points, seed=1234)
-    p = O.make_params(O.dgcnn_seg_param_shapes(3, 4), 1, random_bn=False)
+    if reference_shim.available():
+        ref_dgcnn, _, _ = reference_shim.load()
+        model = ref_dgcnn.DGCNNSeg(k=args.k, in_features=args.in_features, num_classes=4, dynamic=not args.static).to(device)
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+
+        def fwd(x):
+            return model(x)
+        return fwd, opt, "reference"
+    from oracle import dgcnn_oracle as O
+    p = O.make_params(O.dgcnn_seg_param_shapes(args.in_features, 4), 1, random_bn=False)
+    p = {n: v.to(device) for n, v in p.items()}
     params = {n: v.clone().requires_grad_(True) for n, v in p.items() if v.dtype.is_floating_point and "running" not in n}
     state = {n: v for n, v in p.items() if n not in params}
     opt = torch.optim.Adam(list(params.values()), lr=1e-3, weight_decay=1e-5)
+
+    def fwd(x):
+        stats = {}
+        out = O.dgcnn_seg({**state, **params}, x, args.k, dynamic=not args.static, training=True, stats_out=stats)
+        state.update(stats)
+        return out
+    return fwd, opt, "port"
+
+
+def host_memory_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 0.0
+
+
+def cpu_reference_steps(args, batch, steps, warmup, max_seconds):
+    """DGCNNSeg forward + CE + backward + Adam on the host cores, `batch` clouds per step, fp32, autocast off
+    (model_trainer.py:76 disables it on the CPU). Returns (clouds/s, s/step, threads, n_steps, kind)."""
+    from fissure_segmentation_b200 import synth
+    if torch.get_num_threads() < (os.cpu_count() or 1):
+        torch.set_num_threads(os.cpu_count())          # torchrun exports OMP_NUM_THREADS=1: use the whole host anyway
+    x, y = synth.make_batch(batch, args.points, seed=1234, n_features=args.in_features - 3)
+    fwd, opt, kind = build_reference_model(args, "cpu")
     times = []
     t_begin = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        stats = {}
-        logits = O.dgcnn_seg({**state, **params}, x, args.k, dynamic=not args.static, training=True, stats_out=stats)
-        loss = F.cross_entropy(logits, y)
+        loss = F.cross_entropy(fwd(x), y)
         loss.backward()
         opt.step()
         opt.zero_grad()
-        state.update(stats)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
         if time.perf_counter() - t_begin > max_seconds and len(times) >= 2:
             break
     total = sum(times)
-    return B * len(times) / total, total / len(times), torch.get_num_threads(), len(times)
+    return batch * len(times) / total, total / len(times), torch.get_num_threads(), len(times), kind
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, spstep, threads, n = cpu_reference_steps(args, args.steps, args.warmup, max_seconds=240.0)
-    sample = "%d clouds/step x %d steps of the N=%d k=%d workload on the host CPU" % (args.cpu_batch, n, args.points, args.k)
+    if args.workload not in ("train", "configC", "static40"):
+        print(json.dumps({"impl": "reference", "unavailable": "workload %s has no CPU reference arm (pytorch3d / "
+                          "pointops_cuda are CUDA-only third-party dependencies)" % args.workload}), flush=True)
+        return
+    batch = args.cpu_batch
+    if batch is None:
+        # the GPU arm's per-step batch when the host can hold the reference's activations (~0.25 GB per cloud at
+        # N=2048, k=20, fp32), else a smaller bounded sample
+        need_gb = 0.25 * args.batch * (args.points / 2048.0) ** 2 * max(args.k, 20) / 20.0
+        batch = args.batch if host_memory_gb() > 2.0 * need_gb + 8.0 else max(2, min(args.batch, 4))
+    val, spstep, threads, n, kind = cpu_reference_steps(args, batch, args.steps, args.warmup, max_seconds=200.0)
+    sample = ("%d clouds/step x %d timed steps of the N=%d k=%d DGCNNSeg training step on the host CPU (%s, fp32, "
+              "autocast off)" % (batch, n, args.points, args.k,
+                                 "unmodified reference module from baseline/_ref" if kind == "reference" else "oracle port"))
+    cfg = workload_config(args, 1)
+    cfg["cpu_step_batch"] = batch
+    cfg["same_batch_as_gpu_arm"] = batch == args.batch
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
         "warmup": args.warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -165,19 +230,123 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def gpu_eager_baseline(args, dev, steps=8, warmup=3):
+    """The reference module in PyTorch eager on the same B200 (the practical bar): fp32 and fp16 autocast +
+    GradScaler exactly like model_trainer.py:75-76, 154-195, same batch and shape as the measured step."""
+    from fissure_segmentation_b200 import synth
+    x, y = synth.make_batch(args.batch, args.points, seed=1234, n_features=args.in_features - 3)
+    x, y = x.to(dev), y.to(dev)
+    out = {}
+    for mode in ("fp32", "fp16_autocast"):
+        try:
+            fwd, opt, kind = build_reference_model(args, dev)
+            scaler = torch.amp.GradScaler("cuda", enabled=mode != "fp32")
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            for i in range(warmup + steps):
+                if i == warmup:
+                    torch.cuda.synchronize()
+                    ev[0].record()
+                with torch.autocast("cuda", dtype=torch.float16, enabled=mode != "fp32"):
+                    loss = F.cross_entropy(fwd(x), y)
+                scaler.scale(loss).backward()
+                scaler.step(opt)
+                scaler.update()
+                opt.zero_grad()
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / steps
+            out[mode] = {"value": args.batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kind": kind,
+                         "steps": steps, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+        except Exception as exc:           # e.g. out of memory at a large shape: report, do not fail the bench
+            out[mode] = {"unavailable": repr(exc)[:200]}
+        torch.cuda.empty_cache()
+    return out
+
+
 def workload_config(args, world):
-    return {"workload": "DGCNNSeg(k=%d,in_features=3,num_classes=4,%s) train step, batch %d/GPU, N=%d, CE loss, Adam"
-                        % (args.k, "static" if args.static else "dynamic", args.batch, args.points),
-            "global_batch": args.batch * world, "points": args.points, "k": args.k,
+    names = {
+        "train": "DGCNNSeg(k=%d,in_features=3,num_classes=4,%s) train step, batch %d/GPU, N=%d, CE loss, Adam",
+        "configC": "DGCNNSeg(k=%d,in_features=9,num_classes=4,%s) train step (large-cloud kNN stress), batch %d/GPU, N=%d, CE loss, Adam",
+        "static40": "DGCNNSeg(k=%d,in_features=3,num_classes=4,%s) train step (the authors' k=40 static setting), batch %d/GPU, N=%d, CE loss, Adam",
+    }
+    if args.workload in names:
+        wl = names[args.workload] % (args.k, "static" if args.static else "dynamic", args.batch, args.points)
+    elif args.workload == "chamfer":
+        wl = "ChamferLoss forward+backward, %d cloud pairs/GPU, %d vs %d points (PC-AE / DG-SSM loss)" % (args.batch, args.points, args.points)
+    elif args.workload == "pointtransformer":
+        wl = ("reference PointTransformerCompatibility(in_features=3,num_classes=4) fwd+bwd through the reference's "
+              "pointops.py on this package's pointops_cuda, batch %d/GPU, N=%d" % (args.batch, args.points))
+    else:
+        wl = ("predict_full_pointcloud: %d keypoints, 50 eval runs on %d-point subsets (point_seg_net.py:21-48), batched + "
+              "CUDA graph" % (args.points, 2048))
+    return {"workload": wl, "global_batch": args.batch * world, "points": args.points, "k": args.k,
             "parallelism": "dp%d" % world,
             "l2": "no explicit flush: each step streams > 1 GB of activations through the 126 MB L2 and rotates "
                   "through 4 distinct input batches"}
 
 
 # ------------------------------------------------------------------------------------------------
-# our arm
+# roofline bookkeeping: algorithmic work per call of the timed entry points
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def fma_peak_tflops(dev):
+    """Measured FP32 FMA throughput (fs_fma_microbench), best of 5 launches."""
+    from fissure_segmentation_b200 import _lib
+    out = torch.zeros(1, device=dev)
+    iters = 4096
+    flops = 2.0 * 64 * iters * 256 * 148 * 8
+    best = None
+    for _ in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("fs_fma_microbench", out, iters, out, None)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return flops / (best * 1e-3) / 1e12
+
+
+def entry_rooflines(args, timed_ms, hbm_peak, tensor_peak, fma_peak, peak_kind):
+    """One roofline object per timed entry point: algorithmic bytes / flops per call divided by the mean
+    CUDA-event duration of its calls in eager steps of this workload."""
+    B, N, k = args.batch, args.points, args.k
+    P = B * N
+    cp = 64
+    defs = {
+        # feature-space kNN (ec2/ec3 graphs): whole entry point (operand prep + tcgen05 sweeps + finalize)
+        "fs_knn_feat_tc": ("tensor", 2.0 * B * N * N * 64, tensor_peak, "TFLOP/s",
+                           "fs_knn_feat_tc entry point (operand prep + knn_tc_select [tcgen05] + finalize), C=64"),
+        # 3-D kNN: (2C+2) = 8 flops per pair (SURVEY 8d), against the measured FP32 FMA rate
+        "fs_knn3d": ("fp32_fma", 8.0 * B * N * N, fma_peak, "TFLOP/s", "fs_knn3d (coordinate kNN, C=3)"),
+        # EdgeConv gather/max pass, fp32 table: [a|b] 2*Cp*4 + idx 4k + sel 4Cp + arg Cp + sum_y 4Cp bytes per point
+        "fs_edgeconv_gather": ("hbm", float(P) * (2 * cp * 4 + 4 * k + 4 * cp + cp + 4 * cp), hbm_peak, "GB/s",
+                               "fs_edgeconv_gather (ec2/ec3 gather/max pass, Cp=64, train)"),
+        # fused two-layer EdgeConv on coordinates (ec1): layer-2 contraction 2*P*k*64*64 flops on the tensor pipe
+        "fs_edge2_fwd": ("tensor", 2.0 * P * k * 64 * 64, tensor_peak, "TFLOP/s",
+                         "fs_edge2_fwd (fused two-layer EdgeConv forward, tcgen05 64x64 contraction per edge)"),
+        "fs_edge2_bwd": ("tensor", 3 * 2.0 * P * k * 64 * 64, tensor_peak, "TFLOP/s",
+                         "fs_edge2_bwd (fused two-layer EdgeConv backward: recompute + dW2 + dH contractions)"),
+    }
+    out = {}
+    for name, ms_list in timed_ms.items():
+        if name not in defs or not ms_list:
+            continue
+        bound, work, peak, unit, label = defs[name]
+        ms = statistics.mean(ms_list)
+        calls_per_step = len(ms_list) / 3.0
+        achieved = work / (ms * 1e-3) / (1e9 if unit == "GB/s" else 1e12)
+        out[name] = {"kernel": label, "bound": bound, "achieved": achieved, "peak": peak, "peak_kind": peak_kind if bound != "fp32_fma" else "measured (fs_fma_microbench, this run)",
+                     "unit": unit, "frac": achieved / peak if peak else None, "launch_ms": ms,
+                     "calls_per_step": calls_per_step, "ms_per_step": ms * calls_per_step,
+                     ("algorithmic_bytes_per_launch" if unit == "GB/s" else "algorithmic_flops_per_launch"): work,
+                     "launches_timed": len(ms_list), "traffic": None}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm: DGCNNSeg training step (workloads train / configC / static40)
+# ------------------------------------------------------------------------------------------------
+def run_train(args):
     import fissure_segmentation_b200 as fs
     from fissure_segmentation_b200 import _lib, synth
     from fissure_segmentation_b200.ddp import FlatAdam, FlatDataParallel
@@ -196,7 +365,7 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = True
 
     torch.manual_seed(0)
-    model = fs.DGCNNSeg(k=args.k, in_features=3, num_classes=4, dynamic=not args.static).to(dev)
+    model = fs.DGCNNSeg(k=args.k, in_features=args.in_features, num_classes=4, dynamic=not args.static).to(dev)
     model.precision = args.precision
     model.train()
     dp = FlatDataParallel(model, n_buckets=2)
@@ -204,7 +373,8 @@ def run_ours(args):
 
     # synthetic lung-keypoint clouds: 4 distinct batches per rank, pinned on the host
     n_pool = 4
-    pool_h = [synth.make_batch(args.batch, args.points, seed=1234 + rank * 100 + i) for i in range(n_pool)]
+    pool_h = [synth.make_batch(args.batch, args.points, seed=1234 + rank * 100 + i, n_features=args.in_features - 3)
+              for i in range(n_pool)]
     pool_h = [(x.pin_memory(), y.pin_memory()) for x, y in pool_h]
     pool_d = [(x.to(dev), y.to(dev)) for x, y in pool_h]
     x_in = torch.empty_like(pool_d[0][0])
@@ -306,16 +476,16 @@ def run_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    # ---- per-launch duration of the roofline kernels: CUDA events around their launches in eager steps of the same
+    # ---- per-call duration of the roofline entry points: CUDA events around their calls in 3 eager steps of the same
     #      workload (events cannot be read back from inside a replayed graph)
-    _lib.time_calls.update({"fs_edgeconv_gather", "fs_knn_feat_tc"})
+    timed_names = {"fs_edgeconv_gather", "fs_knn_feat_tc", "fs_knn3d", "fs_edge2_fwd", "fs_edge2_bwd"}
+    _lib.time_calls.update(timed_names)
     _lib.timed.clear()
     for i in range(3):
         train_step(*pool_d[i % n_pool])
     barrier()
     _lib.time_calls.clear()
-    gather_ms = [a.elapsed_time(b) for a, b in _lib.timed.get("fs_edgeconv_gather", [])]
-    knn_ms = [a.elapsed_time(b) for a, b in _lib.timed.get("fs_knn_feat_tc", [])]
+    timed_ms = {n: [a.elapsed_time(b) for a, b in v] for n, v in _lib.timed.items()}
     _lib.timed.clear()
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
@@ -325,17 +495,20 @@ def run_ours(args):
     clouds = args.batch * world * args.steps
 
     if rank == 0:
-        hbm_peak, peak_kind = peaks()
-        # dominant HBM kernel: EdgeConv gather pass (ec2/ec3, Cp = 64). Algorithmic bytes per point:
-        # table [a|b] 2*Cp*s + idx 4k + sel 4Cp + arg Cp + sy 4Cp   ("Kernels")
-        s = 4        # the per-point tables are fp32 in every precision mode
-        cp = 64
-        bytes_per_point = 2 * cp * s + 4 * args.k + 4 * cp + cp + 4 * cp
-        alg_bytes = bytes_per_point * args.batch * args.points
-        g_ms = statistics.mean(gather_ms) if gather_ms else None
-        achieved = alg_bytes / (g_ms * 1e-3) / 1e9 if g_ms else None
+        hbm_peak, tensor_peak, peak_kind = peaks()
+        fma_peak = fma_peak_tflops(dev)
+        roofs = entry_rooflines(args, timed_ms, hbm_peak, tensor_peak, fma_peak, peak_kind)
+        prof = {"fs_knn_feat_tc": from_profile("knn_tc_select"), "fs_edgeconv_gather": from_profile("edgeconv_gather"),
+                "fs_edge2_fwd": from_profile("edge2_fwd"), "fs_edge2_bwd": from_profile("edge2_bwd"),
+                "fs_knn3d": from_profile("knn3d")}
+        for name, r in roofs.items():
+            p = prof.get(name)
+            if p is not None:
+                r["traffic"] = p.get("dram_bytes")
+                r["from_profile"] = p
+        metric = METRIC if args.workload == "train" else "point clouds/sec DGCNNSeg fwd+bwd N=%d k=%d" % (args.points, args.k)
         line = {
-            "metric": METRIC, "value": clouds / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": metric, "value": clouds / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
@@ -343,56 +516,196 @@ def run_ours(args):
             "e2e": {"value": clouds / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(x_in.numel() * 4 + y_in.numel() * 8), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "cuda_graph": graph is not None,
-            "clocks": clocks,
-            "roofline": {"kernel": "edgeconv_gather_smem_kernel<16,5,0,float> (ec2/ec3 gather/max pass, Cp=64, train)",
-                         "bound": "hbm", "achieved": achieved,
-                         "peak": hbm_peak, "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": (achieved / hbm_peak) if achieved else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape
-                         # (profiles/r01_g_gather_smem_full.txt): the 37 MB of outputs stay in the 126 MB L2
-                         "traffic": GATHER_DRAM_BYTES if (args.batch, args.points, args.k) == (32, 2048, 20) else None,
-                         "launch_ms": g_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "launches_timed": len(gather_ms)},
+            "clocks": clocks, "fp32_fma_peak_tflops_measured": fma_peak,
         }
-        if knn_ms:
-            # feature-space kNN (ec2/ec3 graphs): the tcgen05 distance GEMM and its selection epilogue, whole entry
-            # point (prep + tensor-core sweeps + finalize). Algorithmic flops 2*B*N^2*C; the kernel issues
-            # 2 sweeps x K = 208 (bf16 hi/lo split) = 6.5x as many.
-            kms = statistics.mean(knn_ms)
-            alg_flops = 2.0 * args.batch * args.points * args.points * 64
-            line["roofline_knn_gemm"] = {
-                "kernel": "fs_knn_feat_tc entry point (tc_colsum + tc_split + knn_tc_select [tcgen05] + knn_tc_finalize)",
-                "bound": "tensor", "achieved": alg_flops / (kms * 1e-3) / 1e12, "peak": TENSOR_PEAK_TFLOPS,
-                "unit": "TFLOP/s", "frac": alg_flops / (kms * 1e-3) / 1e12 / TENSOR_PEAK_TFLOPS,
-                "issued_tflops": alg_flops * 6.5 / (kms * 1e-3) / 1e12, "launch_ms": kms,
-                "tensor_pipe_active_pct_ncu": 43.3, "launches_timed": len(knn_ms)}
+        # `roofline` = the entry point that takes the largest share of the step among this library's timed kernels;
+        # the others follow as roofline_<entry point>
+        if roofs:
+            top = max(roofs, key=lambda n: roofs[n]["ms_per_step"])
+            line["roofline"] = roofs[top]
+            for name, r in roofs.items():
+                if name != top:
+                    line["roofline_" + name[3:]] = r
         if world == 1 and not args.no_cpu_baseline:
-            val, spstep, threads, n = cpu_reference_steps(args, 6, 2, max_seconds=30.0)
+            cb = args.cpu_batch or (8 if args.points <= 2048 else 2)
+            val, spstep, threads, n, kind = cpu_reference_steps(args, cb, 6, 1, max_seconds=30.0)
             line["cpu_baseline"] = {
-                "value": val, "unit": UNIT, "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
-                "sample": "%d clouds/step x %d steps of the same N=%d k=%d training step (oracle port of the "
-                          "reference's PyTorch CPU path, fp32)" % (args.cpu_batch, n, args.points, args.k)}
+                "value": val, "unit": UNIT, "cores": threads, "kind": kind, "host_cpus": os.cpu_count(),
+                "sample": "%d clouds/step x %d steps of the same N=%d k=%d training step (%s, fp32)"
+                          % (cb, n, args.points, args.k, "unmodified reference module, baseline/_ref" if kind == "reference"
+                             else "oracle port of the reference's PyTorch CPU path")}
+        if world == 1 and not args.no_eager_baseline:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(args, dev)
         print(json.dumps(line), flush=True)
+    graph = g = None        # noqa: F841  (closure cells of run_step / e2e_step release the CUDA graph)
+    teardown(world)
+
+
+def teardown(world):
+    """Ordered tear-down of a multi-rank run. The caller has dropped the captured graph (it holds NCCL work of the
+    communicator); here: collect it, drain the device, meet the other ranks, then destroy the process group while every
+    rank is still alive. Round 1 saw communicator destruction dead-lock while a captured graph was alive; a watchdog
+    turns any repeat of that into a plain exit (the result line is already printed and flushed) instead of a hang."""
+    if world <= 1:
+        return
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    watchdog = threading.Timer(20.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    dist.destroy_process_group()
+    watchdog.cancel()
+
+
+# ------------------------------------------------------------------------------------------------
+# other workloads (BASELINE configs[3], [4]; SURVEY 8f rank 4): one JSON line each, same timing rules
+# ------------------------------------------------------------------------------------------------
+def _time_loop(fn, steps, warmup, world):
+    for _ in range(max(warmup, 3)):
+        fn()
     if world > 1:
-        # Tear-down: the captured CUDA graph holds NCCL work of this communicator, and destroying the process group
-        # (or letting the interpreter finalise it) while the graph is alive has been seen to dead-lock after the
-        # result line was printed. Drop the graph, drain the device, meet the other ranks once more and leave
-        # without running the NCCL / CUDA finalisers.
-        graph = None
-        torch.cuda.synchronize()
         dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return ms
+
+
+def run_other(args):
+    import fissure_segmentation_b200 as fs
+    from fissure_segmentation_b200 import _lib, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    hbm_peak, tensor_peak, peak_kind = peaks()
+    sampler = ClockSampler(local)
+    extra = {}
+    steps = min(args.steps, 100)
+    if args.workload == "chamfer":
+        B, N = args.batch, args.points
+        a, b = synth.make_chamfer_pair(B, N, seed=4 + rank)
+        a = a.to(dev).requires_grad_(True)
+        b = b.to(dev)
+        loss_fn = fs.ChamferLoss()
+
+        def fn():
+            a.grad = None
+            loss_fn(a, b).backward()
+        sampler.start()
+        ms = _time_loop(fn, steps, args.warmup, world)
+        unit, value, metric = "cloud pairs/s", B * world * steps / (ms * 1e-3), "Chamfer loss fwd+bwd, %d vs %d points" % (N, N)
+        fma_peak = fma_peak_tflops(dev)
+        _lib.time_calls.add("fs_nn_points")
+        _lib.timed.clear()
+        for _ in range(3):
+            fn()
         torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        _lib.time_calls.clear()
+        nn_ms = [x.elapsed_time(y) for x, y in _lib.timed.get("fs_nn_points", [])]
+        flops = 8.0 * B * N * N
+        t = statistics.mean(nn_ms)
+        extra["roofline"] = {"kernel": "nn_points_kernel (one direction of the Chamfer nearest-neighbour reduction)",
+                             "bound": "fp32_fma", "achieved": flops / (t * 1e-3) / 1e12, "peak": fma_peak,
+                             "peak_kind": "measured (fs_fma_microbench, this run)", "unit": "TFLOP/s",
+                             "frac": flops / (t * 1e-3) / 1e12 / fma_peak, "launch_ms": t, "traffic": None,
+                             "algorithmic_flops_per_launch": flops,
+                             "hbm_frac_secondary": B * 2 * N * 20.0 / (t * 1e-3) / 1e9 / hbm_peak}
+    elif args.workload == "pointtransformer":
+        from oracle import reference_shim            # the reference's own module drives our pointops_cuda kernels
+        _, ref_seg = reference_shim.load_pointtransformer()
+        from fissure_segmentation_b200 import pointops_cuda as pc
+        torch.manual_seed(0)
+        model = ref_seg.PointTransformerCompatibility(in_features=3, num_classes=4).to(dev).train()
+        x, y = synth.make_batch(args.batch, args.points, seed=1234 + rank)
+        x, y = x.to(dev), y.to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+        def fn():
+            opt.zero_grad()
+            F.cross_entropy(model(x), y).backward()
+            opt.step()
+        sampler.start()
+        pc.clear_knn_cache()
+        ms = _time_loop(fn, min(steps, 20), args.warmup, world)
+        steps = min(steps, 20)
+        extra["knn_cache"] = dict(pc.knn_cache_stats)
+        unit, value, metric = UNIT, args.batch * world * steps / (ms * 1e-3), "point clouds/sec PointTransformer seg fwd+bwd N=%d" % args.points
+    else:   # inference
+        torch.manual_seed(0)
+        model = fs.DGCNNSeg(k=args.k, in_features=3, num_classes=4).to(dev).eval()
+        model.precision = args.precision
+        pc_full, _ = synth.make_batch(1, args.points, seed=99)
+        pc_full = pc_full.to(dev)
+        import contextlib
+        import io
+
+        def fn():
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                model.predict_full_pointcloud(pc_full, sample_points=2048, n_runs_min=50)
+        sampler.start()
+        ms = _time_loop(fn, min(steps, 20), args.warmup, world)
+        steps = min(steps, 20)
+        model.inference_cuda_graph = False
+        import fissure_segmentation_b200.modelio as mio
+        seq_ms = None
+        try:
+            batched = mio.PointSegmentationModelBase.predict_full_pointcloud
+
+            def seq():
+                # the reference's sequential loop: 50 B=1 forwards (forced by a batch-of-one per call)
+                with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                    acc = torch.zeros(1, 4, args.points, device=dev)
+                    for _ in range(50):
+                        sub = torch.randperm(args.points, device=dev)[:2048]
+                        acc[..., sub] += torch.softmax(model(pc_full[..., sub]).float(), dim=1)
+            seq_ms = _time_loop(seq, 5, 2, 1) / 5
+            del batched
+        except Exception as exc:
+            extra["sequential_error"] = repr(exc)[:200]
+        extra["sequential_loop_ms_per_cloud"] = seq_ms
+        extra["note"] = ("performance_time_plot.py:31 quotes 0.0009 s for the reference's 'net' stage on other hardware and an "
+                         "unstated configuration; not comparable")
+        unit, value, metric = "full clouds/s", world * steps / (ms * 1e-3), "predict_full_pointcloud, %d keypoints, 50 runs x 2048" % args.points
+    clocks = sampler.stop()
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.workload != "inference" else args.precision, "data": "synthetic",
+                "config": workload_config(args, world), "gpu_launches": int(_lib.launch_count), "clocks": clocks}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    teardown(world)
 
 
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in ("train", "configC", "static40"):
+        run_train(args)
     else:
-        run_ours(args)
+        run_other(args)
 
 
 if __name__ == "__main__":

@@ -722,6 +722,10 @@ extern "C" size_t fs_knn_feat_tc_workspace_bytes(int B, int N, int C, int k) {
     return bytes;
 }
 
+extern "C" size_t fs_knn_feat_tc_redo_offset(int B, int N, int C, int k) {
+    return fs_knn_feat_tc_workspace_bytes(B, N, C, k) - align_up((size_t)B * N, 256);
+}
+
 extern "C" int fs_knn_feat_tc_supported(int B, int N, int C, int k, int self_loop) {
     const int kk = k + (self_loop ? 0 : 1);
     return (C == TC_C && kk <= TC_MAX_KK && N >= 2 * TC_NCLS && N <= 32768 && (long long)B * N <= 0x7fffffff / TC_KROW) ? 1 : 0;

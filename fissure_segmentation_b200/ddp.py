@@ -58,6 +58,7 @@ class FlatDataParallel:
         self._ready = [0] * len(self.buckets)
         self._sent = [False] * len(self.buckets)
         self._works = []
+        self._reduced = False      # True between finish_backward() and zero_grad(): .grad holds all-reduced sums
         if self.world > 1 and broadcast:
             dist.broadcast(self.flat_param, src=0, group=self.group)
         # Gradients are NOT accumulated into the flat buffer by autograd (that costs one add kernel per parameter
@@ -90,6 +91,13 @@ class FlatDataParallel:
                                                async_op=True))
 
     def _hook(self, p):
+        if self._reduced:
+            # Contract: one backward per zero_grad(). After finish_backward() every .grad is a view of the flat
+            # buffer that already holds the SUM over ranks; a second backward would accumulate local gradients on
+            # top of it and reduce the mixture again (silently wrong: ~ world x old + new).
+            raise RuntimeError("FlatDataParallel: backward() after finish_backward() without zero_grad(); gradient "
+                               "accumulation over several backward passes is not supported - call dp.zero_grad() "
+                               "at the start of every step")
         b = self._bucket_of[id(p)]
         self._ready[b] += 1
         if self._ready[b] == self.buckets[b][2] and not self._sent[b]:
@@ -101,6 +109,7 @@ class FlatDataParallel:
     def zero_grad(self):
         for p in self.params:
             p.grad = None
+        self._reduced = False
 
     def finish_backward(self):
         """Flush the buckets whose parameters did not all receive a gradient, wait for the outstanding bucket
@@ -114,6 +123,7 @@ class FlatDataParallel:
         self._works = []
         self._ready = [0] * len(self.buckets)
         self._sent = [False] * len(self.buckets)
+        self._reduced = True
 
 
 class FlatAdam:

@@ -34,7 +34,7 @@ def _compute_dtype(precision):
         return torch.bfloat16
     # 'auto': follow the trainer's autocast context (model_trainer.py:75-76,157); the kernels keep
     # half-precision tables in bf16 whatever the autocast dtype is
-    return torch.bfloat16 if torch.is_autocast_enabled() else torch.float32
+    return torch.bfloat16 if torch.is_autocast_enabled("cuda") else torch.float32
 
 
 def _as_graph(g):
@@ -152,8 +152,8 @@ class EdgeConv(nn.Module):
 
     def forward(self, x, fixed_knn_graph=None):
         B, C, N = x.shape
+        cdt = _compute_dtype(self.precision)         # read the trainer's autocast flag BEFORE it is switched off below
         with torch.autocast("cuda", enabled=False):
-            cdt = _compute_dtype(self.precision)
             out = self.forward_pm(ops.to_point_major(x.float()), B, N, _as_graph(fixed_knn_graph), cdt)
             return out.view(B, N, -1).permute(0, 2, 1).float()
 
@@ -228,8 +228,8 @@ class SpatialTransformer(nn.Module):
     def forward(self, x, fixed_knn_graph=None):
         B, _, N = x.shape
         coords = x[:, :self.in_features].float()
+        cdt = _compute_dtype(self.ec.precision)
         with torch.autocast("cuda", enabled=False):
-            cdt = _compute_dtype(self.ec.precision)
             feat = self.ec.forward_pm(ops.to_point_major(coords), B, N, _as_graph(fixed_knn_graph), cdt)
             feat = self.shared_fc.forward_pool_pm(feat.to(cdt), B, N).float()   # conv + BN + LReLU + max over points
             mat = self.transform(self.mlp(feat)).view(B, self.in_features, self.in_features)
@@ -312,7 +312,7 @@ class DGCNNBase(PointSegmentationModelBase):
 
     def forward(self, x):
         self._perm = None
-        ops.begin_step(x.device)      # one zero-filled arena for all statistics buffers of this step
+        ops.begin_step(x.device, self)      # one zero-filled arena (per model and stream) for all statistics buffers of this step
         if self.spatial_sort and x.is_cuda and x.shape[1] >= 3:
             with torch.no_grad():
                 self._perm = ops.spatial_order(x.detach())
@@ -354,8 +354,8 @@ class DGCNNSeg(DGCNNBase):
     def forward(self, x):
         x = super().forward(x)
         B, _, N = x.shape
+        cdt = _compute_dtype(self.precision)
         with torch.autocast("cuda", enabled=False):
-            cdt = _compute_dtype(self.precision)
             x_pm = ops.to_point_major(x.float())
             g = self._graph if not self.dynamic else None
             x1 = self.ec1.forward_pm(x_pm, B, N, g, cdt)
@@ -399,8 +399,8 @@ class DGCNNReg(DGCNNBase):
     def forward(self, x):
         x = super().forward(x)
         B, _, N = x.shape
+        cdt = _compute_dtype(self.precision)
         with torch.autocast("cuda", enabled=False):
-            cdt = _compute_dtype(self.precision)
             x_pm = ops.to_point_major(x.float())
             g = self._graph if not self.dynamic else None
             x1 = self.ec1.forward_pm(x_pm, B, N, g, cdt)

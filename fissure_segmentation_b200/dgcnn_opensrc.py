@@ -85,10 +85,11 @@ class DGCNN(nn.Module):
         self.dp2 = nn.Dropout(p=args.dropout)
         self.linear3 = nn.Linear(256, output_channels)
 
-    def encode(self, x):
+    def encode(self, x, cdt=None):
         """The four EdgeConv stages: x (B, C, N) -> point-major (B*N, 512)."""
         B, _, N = x.shape
-        cdt = _compute_dtype(self.precision)
+        if cdt is None:
+            cdt = _compute_dtype(self.precision)
         graph = None
         if self.args.static:
             with torch.no_grad():
@@ -102,8 +103,9 @@ class DGCNN(nn.Module):
 
     def forward(self, x):
         B, _, N = x.shape
+        cdt = _compute_dtype(self.precision)          # the autocast flag is read before it is switched off below
         with torch.autocast("cuda", enabled=False):
-            feats = self.encode(x).to(_compute_dtype(self.precision))               # (B*N, 512)
+            feats = self.encode(x, cdt).to(cdt)                                     # (B*N, 512)
             w5 = self.conv5[0].weight.view(self.conv5[0].out_channels, 512)
             e = feats @ w5.to(feats.dtype).t()
             bn = self.bn5

@@ -26,8 +26,18 @@ class KnnGraph:
         self._rev = None
 
     @classmethod
-    def from_reference(cls, idx64):
-        """Accept the reference's (B, N, k) int64 graph (models/dgcnn.py:28-29 fixed_knn_graph)."""
+    def from_reference(cls, idx64, validate=True):
+        """Accept the reference's (B, N, k) int64 graph (models/dgcnn.py:28-29 fixed_knn_graph). The kernels index
+        the tables with these values unchecked, so a user-supplied graph is range-checked here (one min/max
+        reduction; pass validate=False for graphs produced by this package)."""
+        if idx64.dim() != 3 or idx64.dtype not in (torch.int64, torch.int32):
+            raise ValueError("fixed_knn_graph must be an integer (B, N, k) tensor, got %s %s"
+                             % (idx64.dtype, tuple(idx64.shape)))
+        if validate and idx64.numel():
+            lo, hi = torch.aminmax(idx64)
+            if int(lo) < 0 or int(hi) >= idx64.shape[1]:
+                raise IndexError("fixed_knn_graph holds indices outside [0, N=%d): min %d, max %d"
+                                 % (idx64.shape[1], int(lo), int(hi)))
         return cls(idx64.to(torch.int32).contiguous())
 
     def reverse(self):
@@ -64,6 +74,9 @@ def knn_coords(x, k, self_loop=False, diag_zero=True, return_dist=False):
     return (idx, dist) if return_dist else idx
 
 
+knn_tc_report = None      # set to a dict to collect {"rows", "redo_rows"} of every tensor-core kNN call (tests, syncs)
+
+
 def knn_features(feat, B, N, k, self_loop=False, diag_zero=True, return_dist=False):
     """Exact FP32 kNN on a point-major feature table (B*N, C) (row stride arbitrary)."""
     _check_k(k, self_loop, N)
@@ -84,6 +97,11 @@ def knn_features(feat, B, N, k, self_loop=False, diag_zero=True, return_dist=Fal
         ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device)
         _lib.call("fs_knn_feat_tc", feat, feat, feat.stride(0), B, N, C, k, int(self_loop), int(diag_zero), idx, dist,
                   ws, nbytes)
+        if knn_tc_report is not None:
+            off = lib.fs_knn_feat_tc_redo_offset(B, N, C, k)
+            knn_tc_report["rows"] = knn_tc_report.get("rows", 0) + B * N
+            knn_tc_report["redo_rows"] = knn_tc_report.get("redo_rows", 0) + int(ws[off:off + B * N].sum())
+            knn_tc_report["calls"] = knn_tc_report.get("calls", 0) + 1
         return (idx, dist) if return_dist else idx
     ws = torch.empty(B * N, dtype=torch.float32, device=feat.device)
     _lib.call("fs_knn_feat", feat, feat, feat.stride(0), B, N, C, k, int(self_loop), int(diag_zero), idx, dist, ws)
@@ -123,10 +141,12 @@ class _ZeroArena:
 
     def __init__(self):
         self.buf, self.off, self.cap, self.demand = None, 0, 0, 0
+        self.capturing = False       # the buffer belongs to a CUDA graph's private pool
 
     def begin_step(self, device):
         self.cap = max(self.cap, self.demand)
         self.demand, self.off = 0, 0
+        self.capturing = device.type == "cuda" and torch.cuda.is_current_stream_capturing()
         self.buf = torch.zeros(self.cap, dtype=torch.float64, device=device) if self.cap else None
 
     def take(self, n, device):
@@ -139,23 +159,58 @@ class _ZeroArena:
         return torch.zeros(n, dtype=torch.float64, device=device)
 
 
-_arenas = {}
+_arenas = {}          # (device, stream id) -> arena of the step that is running on that stream
 
 
-def begin_step(device):
-    """Start a new zero-filled statistics arena on `device` (called by the networks' forward)."""
+def _arena_key(device):
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device, torch.cuda.current_stream(device).cuda_stream
+
+
+def begin_step(device, owner=None):
+    """Start a new zero-filled statistics arena for the step that runs on the CURRENT stream of `device` (called by
+    the networks' forward). Arenas are keyed by (device, stream), so two models driven from different streams never
+    share a memset; `owner` (the model) keeps the capacity estimate per model."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        return None
+    key = _arena_key(device)
+    arena = getattr(owner, "_fs_arena", None) if owner is not None else _arenas.get(key)
+    if arena is None:
+        arena = _ZeroArena()
+        if owner is not None:
+            owner._fs_arena = arena
+    arena.begin_step(key[0])
+    _arenas[key] = arena
+    return arena
+
+
+def end_step(device):
+    """Detach the arena of the current stream: stand-alone layers (and anything that runs after a CUDA-graph
+    capture, whose arena belongs to the graph's private pool) fall back to individual torch.zeros buffers."""
     device = torch.device(device)
     if device.type != "cuda":
         return
-    _arenas.setdefault(device, _ZeroArena()).begin_step(device)
+    arena = _arenas.pop(_arena_key(device), None)
+    if arena is not None:
+        arena.buf = None
 
 
 def _zeros64(n, device):
-    """n zero-filled 8-byte words (fp64 view) from the step arena."""
-    arena = _arenas.get(torch.device(device))
-    if arena is None:
+    """n zero-filled 8-byte words (fp64 view) from the step arena of the current stream."""
+    device = torch.device(device)
+    arena = _arenas.get(_arena_key(device)) if device.type == "cuda" else None
+    if arena is not None and arena.buf is not None and arena.capturing != torch.cuda.is_current_stream_capturing():
+        # a buffer handed out during a capture lives in the graph's pool and is memset on every replay: never
+        # slice it from eager code (and the other way round)
+        arena = None
+    if arena is None or arena.buf is None:
+        if arena is not None:
+            arena.demand += (n + 1) & ~1
         return torch.zeros(n, dtype=torch.float64, device=device)
-    return arena.take(n, torch.device(device))
+    return arena.take(n, arena.buf.device)
 
 
 def _stats_buffer(C, device):

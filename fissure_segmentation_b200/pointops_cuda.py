@@ -26,9 +26,46 @@ def furthestsampling_cuda(b, n_max, xyz, offset, new_offset, tmp, idx):  # point
     _lib.call("fs_furthestsampling", xyz, int(b), _f32(xyz), _i32(offset), _i32(new_offset), _f32(tmp), _i32(idx))
 
 
+# Per-level kNN cache. The reference's PointTransformerLayer issues the SAME query twice in a row
+# (models/pointtransformer/seg_model.py:38-39: queryandgroup for x_k and again for x_v, identical p / o / nsample), and
+# every block of a level repeats it on unchanged coordinates: 13 distinct of ~44 queries per forward.
+# A hit needs the same storage (data_ptr), the same autograd version counter (no in-place write since) and the same
+# shapes; the cached entry keeps the coordinate tensors alive, so their addresses cannot be recycled for other data.
+KNN_CACHE_SLOTS = 8
+_knn_cache = []            # [(key, (xyz, new_xyz, offset, new_offset), idx, dist2)], most recent last
+knn_cache_stats = {"hits": 0, "misses": 0}
+
+
+def clear_knn_cache():
+    _knn_cache.clear()
+    knn_cache_stats["hits"] = knn_cache_stats["misses"] = 0
+
+
+def _knn_key(m, nsample, xyz, new_xyz, offset, new_offset):
+    return (int(m), int(nsample), xyz.data_ptr(), xyz._version, tuple(xyz.shape), new_xyz.data_ptr(), new_xyz._version,
+            tuple(new_xyz.shape), offset.data_ptr(), offset._version, new_offset.data_ptr(), new_offset._version,
+            torch.cuda.current_stream(xyz.device).cuda_stream)
+
+
 def knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):  # pointops.py:59
-    _lib.call("fs_knnquery", xyz, int(m), int(nsample), _f32(xyz), _f32(new_xyz), _i32(offset), _i32(new_offset),
-              int(offset.shape[0]), _i32(idx), _f32(dist2))
+    _f32(xyz), _f32(new_xyz), _i32(offset), _i32(new_offset), _i32(idx), _f32(dist2)
+    key = _knn_key(m, nsample, xyz, new_xyz, offset, new_offset) if KNN_CACHE_SLOTS > 0 else None
+    if key is not None and not torch.cuda.is_current_stream_capturing():
+        for pos in range(len(_knn_cache) - 1, -1, -1):
+            if _knn_cache[pos][0] == key:
+                entry = _knn_cache.pop(pos)
+                _knn_cache.append(entry)
+                idx.copy_(entry[2])
+                dist2.copy_(entry[3])
+                knn_cache_stats["hits"] += 1
+                return
+    _lib.call("fs_knnquery", xyz, int(m), int(nsample), xyz, new_xyz, offset, new_offset, int(offset.shape[0]), idx,
+              dist2)
+    if key is not None and not torch.cuda.is_current_stream_capturing():
+        knn_cache_stats["misses"] += 1
+        _knn_cache.append((key, (xyz, new_xyz, offset, new_offset), idx.clone(), dist2.clone()))
+        if len(_knn_cache) > KNN_CACHE_SLOTS:
+            _knn_cache.pop(0)
 
 
 def grouping_forward_cuda(m, nsample, c, input, idx, output):  # pointops.py:78

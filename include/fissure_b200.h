@@ -89,6 +89,9 @@ int fs_knn_feat(int device, fs_stream_t stream, const float* x, int ldx, int B, 
  * (C == 64, k + !self_loop <= 32, 64 <= N <= 32768); other shapes run the exact kernel.
  */
 size_t fs_knn_feat_tc_workspace_bytes(int B, int N, int C, int k);
+/* Byte offset, inside the workspace, of the B*N per-row flags (uint8) that are 1 for every query the tensor-core path
+ * handed to the exact kernel (survivor-list overflow, too few survivors, NaN/Inf row). Diagnostics only. */
+size_t fs_knn_feat_tc_redo_offset(int B, int N, int C, int k);
 int fs_knn_feat_tc_supported(int B, int N, int C, int k, int self_loop);
 int fs_knn_feat_tc(int device, fs_stream_t stream, const float* x, int ldx, int B, int N, int C, int k,
                    int self_loop, int diag_zero, int32_t* idx, float* dist2, void* workspace,
@@ -354,6 +357,29 @@ int fs_aggregation_bwd(int device, fs_stream_t stream, int n, int nsample, int c
 int fs_adam_step(int device, fs_stream_t stream, float* param, const float* grad, float* exp_avg,
                  float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int step, float grad_scale, const float* dyn_step_lr);
+
+/* ---------------------------------------------------------------- ensemble inference ------- */
+
+/*
+ * acc[c][sub[r][s]] += softmax_c(logits[r][:, s]) for all R runs of
+ * models/point_seg_net.py:27-29 and :43 (`softmax_accumulation[..., perm] += output_activation(self(pc[..., perm]))`)
+ * in one launch, the R subset forwards having been batched into one B = R forward.
+ *   logits [R, classes, S]  fp32, the network output (B x classes x N layout)
+ *   sub    [R, S]           int64 point indices into the full cloud (unique within a run)
+ *   acc    [classes, n_total] fp32, accumulated in place (fp32 atomics: order over the runs is not fixed)
+ * classes <= 32.
+ */
+int fs_softmax_scatter_add(int device, fs_stream_t stream, const float* logits, const long long* sub, int R,
+                           int classes, int S, int n_total, float* acc);
+
+/* ---------------------------------------------------------------- measurement -------------- */
+
+/*
+ * FP32 FMA throughput micro-benchmark (one launch of 148 x 8 CTAs x 256 threads x iters x 64 dependent-chain FMAs,
+ * ILP 8): the measured roofline denominator for the CUDA-core kernels (fs_knn3d, fs_nn_points). `out` is a device
+ * scalar that is never written in practice; *flops_out (HOST pointer, nullable) receives the flops of the launch.
+ */
+int fs_fma_microbench(int device, fs_stream_t stream, int iters, float* out, double* flops_out);
 
 #ifdef __cplusplus
 }

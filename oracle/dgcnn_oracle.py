@@ -215,3 +215,31 @@ def opensrc_stage(x_bcn, p, conv, bn, k, idx, training):
     rm, rv = p[bn + ".running_mean"].clone(), p[bn + ".running_var"].clone()
     e = F.batch_norm(e, rm, rv, p[bn + ".weight"], p[bn + ".bias"], training, BN_MOMENTUM, BN_EPS)
     return F.leaky_relu(e, LEAKY).max(dim=-1)[0]
+
+
+# ----------------------------------------------------------------------------------------------
+# PointSegmentationModelBase.predict_full_pointcloud (models/point_seg_net.py:21-48)
+# ----------------------------------------------------------------------------------------------
+def predict_full_pointcloud(forward, pc, num_classes, sample_points=1024, n_runs_min=50, randperm=torch.randperm):
+    """Restatement of models/point_seg_net.py:21-48 over a forward callable `forward(x: 1 x C x n) -> logits`.
+    `randperm(n)` is injectable so that a test can draw the permutations from the same (device) generator stream
+    as the implementation under test; draws happen in the reference's order. Includes the reference's quirk at :41-43
+    of indexing the point cloud with positions *into* `other_pts` rather than with `other_pts[...]`."""
+    n_leftover = n_runs_min // 5                                             # :24
+    n_initial = n_runs_min - n_leftover                                      # :25
+    acc = torch.zeros(pc.shape[0], num_classes, *pc.shape[2:])               # :26
+    for _ in range(n_initial):                                               # :27-29
+        perm = randperm(pc.shape[-1])[:sample_points]
+        acc[..., perm] += torch.softmax(forward(pc[..., perm]), dim=1)
+    left_out = torch.nonzero(acc.sum(1) == 0)[..., 1]                        # :32
+    if left_out.shape[0] > 0:
+        other = torch.nonzero(acc.sum(1))[..., 1]                            # :35
+        point_mix = sample_points // 2
+        fill_out = sample_points - point_mix
+        perm = randperm(n_leftover * point_mix) % len(left_out)              # :38
+        for r in range(n_leftover):
+            lo = left_out[perm[r * point_mix:(r + 1) * point_mix]]
+            oth = randperm(len(other))[:fill_out]                            # :41 (positions, not other[...])
+            pts = torch.cat((lo, oth), dim=0)
+            acc[..., pts] += torch.softmax(forward(pc[..., pts]), dim=1)     # :43
+    return torch.softmax(acc, dim=1)                                         # :48

@@ -1,5 +1,5 @@
 """Golden fixtures for the secondary model classes (DGCNNReg, DGCNNSeg with spatial transformer + image-feature
-module, dgcnn_opensrc.DGCNN), produced by the UNMODIFIED reference (/root/reference).
+module, dgcnn_opensrc.DGCNN, folding_net.DGCNN_Cls_Encoder), produced by the UNMODIFIED reference (/root/reference).
 
 Run in the build container only:  python tests/golden/make_golden_models.py
 """
@@ -25,6 +25,9 @@ def build_reference(cfg, ref_dgcnn, ref_opensrc):
         m = ref_dgcnn.DGCNNReg(**cfg["kwargs"])
     elif cfg["kind"] == "seg":
         m = ref_dgcnn.DGCNNSeg(**cfg["kwargs"])
+    elif cfg["kind"] == "cls_encoder":
+        import models.folding_net as ref_folding          # /root/reference, through the same shims
+        m = ref_folding.DGCNN_Cls_Encoder(**cfg["kwargs"])
     else:
         m = ref_opensrc.DGCNN(MF.opensrc_args(cfg), cfg["in_features"], cfg["output_channels"])
     return MF.perturb(m, cfg["seed"])

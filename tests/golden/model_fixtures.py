@@ -18,6 +18,11 @@ CONFIGS = {
     # models/dgcnn_opensrc.py:101-179 - the open-source DGCNN used by DG-SSM / affine DGCNN (dropout 0: deterministic)
     "opensrc_static": dict(kind="opensrc", seed=47, B=4, N=256, in_features=3, data_seed=57,
                            args=dict(k=8, emb_dims=128, dropout=0.0, static=True), output_channels=5),
+    # models/folding_net.py:83-141 - PC-AE encoder (DGCNN_Cls_Encoder), static coordinate graph and dynamic graphs
+    "cls_encoder_static": dict(kind="cls_encoder", seed=59, B=4, N=256, in_features=3, data_seed=61,
+                               kwargs=dict(k=8, n_embedding=128, static=True)),
+    "cls_encoder_dynamic": dict(kind="cls_encoder", seed=67, B=2, N=512, in_features=3, data_seed=71,
+                                kwargs=dict(k=12, n_embedding=256, static=False)),
 }
 
 

@@ -31,6 +31,9 @@ def build_ours(cfg):
         m = fs.DGCNNReg(**cfg["kwargs"])
     elif cfg["kind"] == "seg":
         m = fs.DGCNNSeg(**cfg["kwargs"])
+    elif cfg["kind"] == "cls_encoder":
+        from fissure_segmentation_b200.folding_net import DGCNN_Cls_Encoder
+        m = DGCNN_Cls_Encoder(**cfg["kwargs"])
     else:
         m = dgcnn_opensrc.DGCNN(MF.opensrc_args(cfg), cfg["in_features"], cfg["output_channels"])
     return MF.perturb(m, cfg["seed"])
