@@ -207,13 +207,18 @@ bn_act_bwd_apply_kernel(const GT* __restrict__ g, int ldg, const T* __restrict__
     constexpr int V = 4;
     RowMap m(C, V);
     for (int cc = m.c0; cc < C; cc += m.tpr * V) {
-        float mu[V], inv[V], sc[V], be[V], mb[V], mg[V];
+        // mean(d) and mean(d xhat) as hi + lo float pairs: the per-cloud sums of dx (the gradient of a per-cloud bias
+        // row, i.e. of the global feature) cancel to rounding level, so an fp32-rounded mean would leave a systematic
+        // residue of rows * ulp(mean) in them
+        float mu[V], inv[V], sc[V], be[V], mb[V], mg[V], mbl[V], mgl[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             mu[i] = __ldg(coef + cc + i); inv[i] = __ldg(coef + C + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i);
             be[i] = __ldg(coef + 3 * C + cc + i);
-            mb[i] = train_stats ? (float)(dgb[cc + i] / count) : 0.f;
-            mg[i] = train_stats ? (float)(dgb[C + cc + i] / count) * inv[i] : 0.f;
+            const double mbd = train_stats ? dgb[cc + i] / count : 0.0;
+            const double mgd = train_stats ? dgb[C + cc + i] / count * (double)inv[i] : 0.0;
+            mb[i] = (float)mbd; mbl[i] = (float)(mbd - (double)mb[i]);
+            mg[i] = (float)mgd; mgl[i] = (float)(mgd - (double)mg[i]);
         }
         for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += (long long)gridDim.x * m.rows_per_pass) {
             float gv[V], f[V], o[V];
@@ -237,7 +242,7 @@ bn_act_bwd_apply_kernel(const GT* __restrict__ g, int ldg, const T* __restrict__
                 const float xc = f[i] - mu[i];
                 const float z = fmaf(sc[i], xc, be[i]);
                 const float d = z > 0.f ? gv[i] : slope * gv[i];
-                o[i] = sc[i] * (d - mb[i] - mg[i] * xc);
+                o[i] = sc[i] * (((d - mb[i]) - mbl[i]) - fmaf(mgl[i], xc, mg[i] * xc));
             }
             if (sizeof(OT) == 4) Vec<float>::store(reinterpret_cast<float*>(dx) + row * ld_dx + cc, o);
             else {

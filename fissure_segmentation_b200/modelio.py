@@ -80,7 +80,8 @@ class PointSegmentationModelBase(LoadableModel, ABC):
         cache = self.__dict__.setdefault("_infer_graphs", {})
         entry = cache.get(key)
         if entry is None:
-            cache.clear()
+            if len(cache) >= 4 or any(k[3] != key[3] for k in cache):     # other weights storage: drop stale graphs
+                cache.clear()
             static_x = x.clone()
             side = torch.cuda.Stream(device=x.device)
             side.wait_stream(torch.cuda.current_stream(x.device))

