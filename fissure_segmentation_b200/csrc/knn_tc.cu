@@ -108,25 +108,29 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Spin on the phase parity. The spin is bounded: a protocol bug traps (the launch fails with an error the host sees)
-// instead of hanging the GPU. try_wait itself suspends the thread for a hardware-defined time slice, so the counter is
-// cheap; the limit (2^22 polls: seconds) is far beyond any legitimate wait. -DFS_TC_UNBOUNDED_WAIT removes the counter.
+// Wait on the phase parity. try_wait suspends the thread in hardware until the phase completes or the time hint (about
+// 1 ms) runs out, so a waiting warp does not burn issue slots of the other CTA on the SM. The wait is bounded: a protocol
+// bug traps after 2^12 time-outs (seconds; the launch fails with an error the host sees) instead of hanging the GPU.
+// -DFS_TC_UNBOUNDED_WAIT removes the counter.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
 #ifndef FS_TC_UNBOUNDED_WAIT
     uint32_t polls = 0;
 #endif
-    while (true) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
+    while (!mbar_try_wait(bar, parity)) {
 #ifndef FS_TC_UNBOUNDED_WAIT
-        if (++polls > (1u << 22)) __trap();
+        if (++polls > (1u << 12)) __trap();
 #endif
     }
 }
@@ -247,68 +251,84 @@ __device__ __forceinline__ void tc_extras(float nrm, __half* ea, __half* eb) {
 // scale of a cloud: centred values lie in [-2 amax, 2 amax] -> [-1, 1]
 __device__ __forceinline__ float tc_inv_scale(float amax) { return amax > 0.f ? 0.5f / amax : 1.0f; }
 
-// Feature rows (C = 64 / 128 / 256): one warp per row, four rows per warp. The raw squared norm is summed exactly like
-// row_sqnorm_kernel (knn.cu) so the exact re-evaluation matches the exact kernel bit for bit.
-constexpr int TC_SPLIT_ROWS = 4;
+// Feature rows (C = 64 CH, CH = 1 / 2 / 4): one warp per row, ROWS = 4 / CH rows per warp with all their loads in
+// flight together. The raw squared norm is summed exactly like row_sqnorm_kernel (knn.cu) so the exact re-evaluation
+// matches the exact kernel bit for bit.
+template <int CH>
 __global__ void __launch_bounds__(256)
 tc_split_feat_kernel(const float* __restrict__ x, int ldx, long long P, int N, TcShape sh, float* __restrict__ stats,
                      __half* __restrict__ A, __half* __restrict__ Bm, float* __restrict__ cnorm, float* __restrict__ sqnorm) {
+    constexpr int ROWS = 4 / CH;
+    constexpr int C = 64 * CH;
     __shared__ int s_max[2];
-    const int C = sh.C;
-    const long long blk_row0 = (long long)blockIdx.x * 8 * TC_SPLIT_ROWS;
-    const long long blk_row1 = blk_row0 + 8 * TC_SPLIT_ROWS - 1 < P - 1 ? blk_row0 + 8 * TC_SPLIT_ROWS - 1 : P - 1;
+    const long long blk_row0 = (long long)blockIdx.x * 8 * ROWS;
+    const long long blk_row1 = blk_row0 + 8 * ROWS - 1 < P - 1 ? blk_row0 + 8 * ROWS - 1 : P - 1;
     const bool one_cloud = blk_row0 / N == blk_row1 / N;
     if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
     __syncthreads();
-    const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * TC_SPLIT_ROWS;
+    const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * ROWS;
     const int lane = threadIdx.x & 31;
     const float inv_n = 1.0f / (float)N;
-    const int sstride = tc_stats_stride(C);
+    constexpr int sstride = C + 4;
     const __half2 m2 = __float2half2_rn(-2.0f);
-    for (int r = 0; r < TC_SPLIT_ROWS; ++r) {
-        const long long row = row0 + r;
-        if (row >= P) break;                                    // warp-uniform
-        const int b = (int)(row / N);
-        const float* st = stats + (long long)b * sstride;
-        const float inv_s = tc_inv_scale(__int_as_float(__ldg(reinterpret_cast<const int*>(st + C))));
-        float nrm = 0.f, raw = 0.f;
-        __half2* Ar = reinterpret_cast<__half2*>(A + row * sh.krow);
-        __half2* Br = reinterpret_cast<__half2*>(Bm + row * sh.krow);
-        for (int c0 = 0; c0 < C; c0 += 64) {
-            const float2 xv = __ldg(reinterpret_cast<const float2*>(x + row * ldx + c0 + 2 * lane));
-            const float ra = __ldg(x + row * ldx + c0 + lane), rb = __ldg(x + row * ldx + c0 + lane + 32);
-            raw = __fadd_rn(__fadd_rn(raw, __fmul_rn(ra, ra)), __fmul_rn(rb, rb));     // channels lane, lane+32, lane+64, ...
-            const float v0 = (xv.x - __ldg(st + c0 + 2 * lane) * inv_n) * inv_s;
-            const float v1 = (xv.y - __ldg(st + c0 + 2 * lane + 1) * inv_n) * inv_s;
-            const __half2 hh = __floats2half2_rn(v0, v1);
-            const float2 e = __half22float2(hh);
-            nrm = fmaf(e.x, e.x, fmaf(e.y, e.y, nrm));
-            Ar[(c0 >> 1) + lane] = hh;
-            Br[(c0 >> 1) + lane] = __hmul2(hh, m2);
-        }
-        nrm = fs_warp_sum(nrm);
-        raw = fs_warp_sum(raw);
-        // extras box: 16 halfs are read by the MMA (6 meaningful); lanes 0..7 write them
-        if (lane < 8) {
-            __half ea[8], eb[8];
-            tc_extras(nrm, ea, eb);
-            ea[6] = ea[7] = eb[6] = eb[7] = __float2half_rn(0.f);
-            __half a0 = __float2half_rn(0.f), a1 = a0, b0 = a0, b1 = a0;
+    if (row0 < P) {
+        float2 xv[ROWS][CH];
+        float ra[ROWS][CH], rb[ROWS][CH];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (lane == i) { a0 = ea[2 * i]; a1 = ea[2 * i + 1]; b0 = eb[2 * i]; b1 = eb[2 * i + 1]; }
-            Ar[(C >> 1) + lane] = __halves2half2(a0, a1);
-            Br[(C >> 1) + lane] = __halves2half2(b0, b1);
+        for (int r = 0; r < ROWS; ++r) {
+            const long long row = row0 + r < P ? row0 + r : P - 1;
+#pragma unroll
+            for (int h = 0; h < CH; ++h) {
+                xv[r][h] = __ldg(reinterpret_cast<const float2*>(x + row * ldx + 64 * h + 2 * lane));
+                ra[r][h] = __ldg(x + row * ldx + 64 * h + lane);
+                rb[r][h] = __ldg(x + row * ldx + 64 * h + lane + 32);
+            }
         }
-        if (lane == 0) {
-            cnorm[row] = nrm;
-            sqnorm[row] = raw;
-            if (one_cloud) {
-                atomicMax(&s_max[0], __float_as_int(nrm));
-                atomicMax(&s_max[1], __float_as_int(raw));
-            } else {
-                atomicMax(reinterpret_cast<int*>(stats + (long long)b * sstride + C + 1), __float_as_int(nrm));
-                atomicMax(reinterpret_cast<int*>(stats + (long long)b * sstride + C + 2), __float_as_int(raw));
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const long long row = row0 + r;
+            if (row >= P) break;                                    // warp-uniform
+            const int b = (int)(row / N);
+            const float* st = stats + (long long)b * sstride;
+            const float inv_s = tc_inv_scale(__int_as_float(__ldg(reinterpret_cast<const int*>(st + C))));
+            float nrm = 0.f, raw = 0.f;
+            __half2* Ar = reinterpret_cast<__half2*>(A + row * sh.krow);
+            __half2* Br = reinterpret_cast<__half2*>(Bm + row * sh.krow);
+#pragma unroll
+            for (int h = 0; h < CH; ++h) {
+                raw = __fadd_rn(__fadd_rn(raw, __fmul_rn(ra[r][h], ra[r][h])), __fmul_rn(rb[r][h], rb[r][h]));   // channels lane, lane+32, ...
+                const float v0 = (xv[r][h].x - __ldg(st + 64 * h + 2 * lane) * inv_n) * inv_s;
+                const float v1 = (xv[r][h].y - __ldg(st + 64 * h + 2 * lane + 1) * inv_n) * inv_s;
+                const __half2 hh = __floats2half2_rn(v0, v1);
+                const float2 e = __half22float2(hh);
+                nrm = fmaf(e.x, e.x, fmaf(e.y, e.y, nrm));
+                Ar[32 * h + lane] = hh;
+                Br[32 * h + lane] = __hmul2(hh, m2);
+            }
+            nrm = fs_warp_sum(nrm);
+            raw = fs_warp_sum(raw);
+            // extras box: the whole 128-byte box is written (16 halfs are read by the MMA, 6 of them meaningful)
+            {
+                __half ea[8], eb[8];
+                tc_extras(nrm, ea, eb);
+                ea[6] = ea[7] = eb[6] = eb[7] = __float2half_rn(0.f);
+                __half a0 = __float2half_rn(0.f), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (lane == i) { a0 = ea[2 * i]; a1 = ea[2 * i + 1]; b0 = eb[2 * i]; b1 = eb[2 * i + 1]; }
+                Ar[(C >> 1) + lane] = __halves2half2(a0, a1);
+                Br[(C >> 1) + lane] = __halves2half2(b0, b1);
+            }
+            if (lane == 0) {
+                cnorm[row] = nrm;
+                sqnorm[row] = raw;
+                if (one_cloud) {
+                    atomicMax(&s_max[0], __float_as_int(nrm));
+                    atomicMax(&s_max[1], __float_as_int(raw));
+                } else {
+                    atomicMax(reinterpret_cast<int*>(stats + (long long)b * sstride + C + 1), __float_as_int(nrm));
+                    atomicMax(reinterpret_cast<int*>(stats + (long long)b * sstride + C + 2), __float_as_int(raw));
+                }
             }
         }
     }
@@ -363,14 +383,31 @@ tc_split_xyz_kernel(const float* __restrict__ coords, long long batch_stride, lo
 #pragma unroll
     for (int i = 0; i < TC_EXTRAS; ++i) { ra[9 + i] = ea[i]; rb[9 + i] = eb[i]; }
     ra[15] = zero; rb[15] = zero;
+    // the whole 128-byte operand row is written (TMA reads whole rows; only the first 16 halfs enter the MMA)
     uint4* Ar = reinterpret_cast<uint4*>(A + row * sh.krow);
     uint4* Br = reinterpret_cast<uint4*>(Bm + row * sh.krow);
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
     Ar[0] = *reinterpret_cast<uint4*>(ra); Ar[1] = *reinterpret_cast<uint4*>(ra + 8);
     Br[0] = *reinterpret_cast<uint4*>(rb); Br[1] = *reinterpret_cast<uint4*>(rb + 8);
+#pragma unroll
+    for (int i = 2; i < 8; ++i) { Ar[i] = z4; Br[i] = z4; }
     cnorm[row] = nrm;
     sqnorm[row] = raw;
-    atomicMax(reinterpret_cast<int*>(st + 4), __float_as_int(nrm));
-    atomicMax(reinterpret_cast<int*>(st + 5), __float_as_int(raw));
+    // per-cloud maxima: one atomic per warp when the warp's rows share a cloud (per-thread atomics serialise)
+    const unsigned act = __activemask();
+    const int b0 = __shfl_sync(act, b, __ffs(act) - 1);
+    if (__all_sync(act, b == b0)) {
+        int mn = __float_as_int(nrm), mr = __float_as_int(raw);
+        mn = __reduce_max_sync(act, mn);
+        mr = __reduce_max_sync(act, mr);
+        if ((int)(threadIdx.x & 31) == __ffs(act) - 1) {
+            atomicMax(reinterpret_cast<int*>(st + 4), mn);
+            atomicMax(reinterpret_cast<int*>(st + 5), mr);
+        }
+    } else {
+        atomicMax(reinterpret_cast<int*>(st + 4), __float_as_int(nrm));
+        atomicMax(reinterpret_cast<int*>(st + 5), __float_as_int(raw));
+    }
 }
 
 // Per-row error terms (scaled, centred units): e = sqrt-space margin, g = linear margin.
@@ -463,14 +500,22 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
         // ===================== TMA producer =====================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+            // A stage is free once the MMAs of the tile that used it have completed - exactly what that tile's acc_full
+            // barrier signals - so the issuer does not spend a second tcgen05.commit per tile on a stage-empty barrier
+            // (a commit costs the single issuing thread ~200 cycles, and that thread is the serial bottleneck).
+            int s = 0, tile = 0, ra = 0;
+            uint32_t rph = 0;
             for (int it = 0; it < 2 * T; ++it) {
-                const int s = it % sh.stages;
-                const uint32_t ph = (it / sh.stages) & 1;
-                mbar_wait(smem_u32(b_empty + s), ph ^ 1);
+                if (it >= sh.stages) {                 // tile it - stages used this stage: wait for its accumulator-full
+                    mbar_wait(smem_u32(acc_full + ra), rph);
+                    if (++ra == sh.nacc) { ra = 0; rph ^= 1; }
+                }
                 mbar_expect_tx(smem_u32(b_full + s), stage_bytes);
-                const int row = (int)(cloud0 + (it % T) * TC_NB);
+                const int row = (int)(cloud0 + tile * TC_NB);
                 for (int bx = 0; bx < sh.nboxes; ++bx)
                     tma_load_2d(smem_u32(smem_b + s * stage_bytes + bx * TC_BOX_BYTES), &map_b, smem_u32(b_full + s), bx * 64, row);
+                if (++s == sh.stages) s = 0;
+                if (++tile == T) tile = 0;
             }
         }
     } else if (warp == TC_WARP_MMA) {
@@ -478,16 +523,16 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
         mbar_wait(smem_u32(a_full), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b));
+        int s = 0, a = 0;
+        uint32_t ph_s = 0, ph_a = 0;
         for (int it = 0; it < 2 * T; ++it) {
             if (it == T) {
                 // sweep 2 multiplies the thresholds the epilogue wrote into the query operand: wait for all rows
                 mbar_wait(smem_u32(a2_full), 0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            const int s = it % sh.stages;
-            const int a = it % sh.nacc;
-            mbar_wait(smem_u32(b_full + s), (it / sh.stages) & 1);            // operands landed
-            mbar_wait(smem_u32(acc_empty + a), ((it / sh.nacc) & 1) ^ 1);     // accumulator buffer drained by the epilogue
+            mbar_wait(smem_u32(b_full + s), ph_s);            // operands landed
+            mbar_wait(smem_u32(acc_empty + a), ph_a ^ 1);     // accumulator buffer drained by the epilogue
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one_sync()) {
                 const uint64_t db_s = db0 + (uint64_t)((s * stage_bytes) >> 4);
@@ -496,10 +541,11 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
                     const uint64_t db = db_s + (uint64_t)((tc_step_box(sh, st) * TC_BOX_BYTES + tc_step_off(sh, st)) >> 4);
                     umma_f16_ts(acc_a, tmem_base + st * 8, db, st ? 1u : 0u);
                 }
-                umma_commit(smem_u32(b_empty + s));         // smem stage free once these MMAs retire
                 umma_commit(smem_u32(acc_full + a));        // accumulator ready
             }
             __syncwarp();
+            if (++s == sh.stages) { s = 0; ph_s ^= 1; }
+            if (++a == sh.nacc) { a = 0; ph_a ^= 1; }
         }
     } else {
         // ===================== epilogue: TMEM lane = query row; two warps share a row, one per 32-column half ======
@@ -533,11 +579,12 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
 #pragma unroll
         for (int e = 0; e < 32; ++e) gm[e] = INFINITY;
         int cnt = 0;
-        const long long out_base = (cloud0 + (row_ok ? qrow : 0)) * TC_CAP + cb * (TC_CAP / TC_HALVES);
+        int32_t* const out_j = cand_j + (cloud0 + (row_ok ? qrow : 0)) * TC_CAP + cb * (TC_CAP / TC_HALVES);
+        float* const out_d = cand_d + (cloud0 + (row_ok ? qrow : 0)) * TC_CAP + cb * (TC_CAP / TC_HALVES);
+        const int diag_jb = diag_zero ? q_row0 + w4 * 32 : -1;       // candidate block that holds this warp's diagonal
+        int a = 0, jb = cb * 32;
+        uint32_t ph = 0;
         for (int it = 0; it < 2 * T; ++it) {
-            const int a = it % sh.nacc;
-            const uint32_t ph = (it / sh.nacc) & 1;
-            const int jb = (it % T) * TC_NB + cb * 32;
             if (it == T) {
                 // between the sweeps: the two column halves of a row hold 32 class minima each over DISJOINT candidate
                 // sets = 64 classes. Each thread sorts its own 32, the pair exchanges them through the staging blocks
@@ -621,7 +668,7 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] = (jb + e < N) ? v[e] : INFINITY;
             }
-            if (diag_zero && jb == q_row0 + w4 * 32) {      // warp-uniform: this block holds the warp's diagonal
+            if (jb == diag_jb) {      // warp-uniform: this block holds the warp's diagonal
                 // the reference forces d(i,i) = 0 (general_utils.py:52): the query itself always survives
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] = (jb + e == qrow) ? -FLT_MAX : v[e];
@@ -648,13 +695,16 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
                         hits &= hits - 1;
                         const float dv = stage[(((e >> 2) ^ (lane & 7)) << 2) + (e & 3)];
                         if (cnt < TC_CAP / TC_HALVES) {
-                            cand_j[out_base + cnt] = jb + e;
-                            cand_d[out_base + cnt] = dv;
+                            out_j[cnt] = jb + e;
+                            out_d[cnt] = dv;
                         }
                         ++cnt;
                     }
                 }
             }
+            if (++a == sh.nacc) { a = 0; ph ^= 1; }
+            jb += TC_NB;
+            if (it == T - 1) jb = cb * 32;
         }
         if (row_ok) cand_n[(cloud0 + qrow) * TC_HALVES + cb] = cnt;
     }
@@ -677,6 +727,7 @@ struct TcExactFeat {
     __device__ __forceinline__ float operator()(const float* xq, float qq, long long cloud0, int q, int j, int diag_zero) const {
         const float* xr = x + (cloud0 + j) * ldx;
         float acc = 0.f;
+#pragma unroll 8
         for (int c4 = 0; c4 < C / 4; ++c4) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + c4);
             acc = fmaf(xq[4 * c4], v.x, acc);
@@ -1009,7 +1060,9 @@ extern "C" int fs_knn_feat_tc(int device, fs_stream_t stream_, const float* x, i
     // 1. prep: per-cloud column sums and absolute maximum, then the fp16 operand tables
     FS_CUDA_TRY(cudaMemsetAsync(w.stats, 0, w.stats_bytes, stream));
     tc_cloud_stats_kernel<<<dim3(32, B), 256, 0, stream>>>(x, (long long)N * ldx, ldx, 1, N, C, w.stats);
-    tc_split_feat_kernel<<<fs_div_up(P, 8 * TC_SPLIT_ROWS), 256, 0, stream>>>(x, ldx, P, N, sh, w.stats, w.A, w.Bm, w.cnorm, w.sqnorm);
+    if (C == 64) tc_split_feat_kernel<1><<<fs_div_up(P, 32), 256, 0, stream>>>(x, ldx, P, N, sh, w.stats, w.A, w.Bm, w.cnorm, w.sqnorm);
+    else if (C == 128) tc_split_feat_kernel<2><<<fs_div_up(P, 16), 256, 0, stream>>>(x, ldx, P, N, sh, w.stats, w.A, w.Bm, w.cnorm, w.sqnorm);
+    else tc_split_feat_kernel<4><<<fs_div_up(P, 8), 256, 0, stream>>>(x, ldx, P, N, sh, w.stats, w.A, w.Bm, w.cnorm, w.sqnorm);
     FS_RETURN_IF_LAUNCH_FAILED();
     // 2. tensor-core sweeps, 3. finalize
     int e = tc_run<false>(stream, sh, w, x, ldx, B, N, k, self_loop, diag_zero, idx);
@@ -1037,8 +1090,6 @@ extern "C" int fs_knn3d_tc(int device, fs_stream_t stream_, const float* coords,
     const long long P = (long long)B * N;
     const TcWorkspace w = tc_carve(workspace, B, N, sh);
     FS_CUDA_TRY(cudaMemsetAsync(w.stats, 0, w.stats_bytes, stream));
-    // only 16 of the 64 halfs of an operand row are written by the split kernel; TMA reads whole 128-byte rows
-    FS_CUDA_TRY(cudaMemsetAsync(w.A, 0, 2 * align_up(w.table_bytes, 256), stream));
     tc_cloud_stats_kernel<<<dim3(16, B), 192, 0, stream>>>(coords, batch_stride, point_stride, chan_stride, N, 3, w.stats);
     tc_split_xyz_kernel<<<fs_div_up(P, 256), 256, 0, stream>>>(coords, batch_stride, chan_stride, point_stride, P, N, sh, w.stats,
                                                               w.A, w.Bm, w.cnorm, w.sqnorm, w.xyz_pm);

@@ -371,6 +371,27 @@ int fs_adam_step(int device, fs_stream_t stream, float* param, const float* grad
                  float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int step, float grad_scale, const float* dyn_step_lr);
 
+/* ---------------------------------------------------------------- fused two-layer EdgeConv --- */
+
+/*
+ * Two-layer EdgeConv on raw coordinates, forward (models/dgcnn.py:119 `ec1 = EdgeConv(in_features, [64, 64])` with the
+ * 3-channel coordinate input; loop at :237-241): neither the hidden edge tensor H (P*k x 64) nor the layer-2
+ * pre-activation Z is written. Layer 1 (Conv 6->64 + BatchNorm + LeakyReLU) is recomputed from the coordinates with
+ * the coefficients of fs_edge3_bn_coef; layer 2 (64 -> C2) runs as tcgen05.mma on bf16 tiles of H staged in shared
+ * memory, transposed so that a TMEM lane is an output channel and the max over the k edges of a point is a
+ * per-thread reduction.
+ *   w1 [64,6], coef1 [4*64] (mu | 1/sigma | gamma/sigma | beta), w2 [C2,64] fp32, gamma2 [C2] (sign selects max / min)
+ *   sel [P,C2] fp32 selected pre-activation, arg [P,C2] uint8 slot of the selected edge
+ *   stats (nullable = eval): fs_stats_buffer_doubles(C2) doubles, zero-filled: sum z, sum z^2 over all P*k edges
+ *   gram [64*64], hsum [64] (required with stats, zero-filled): sum_e h_e h_e^T and sum_e h_e (bf16-rounded h), which
+ *   the BatchNorm coupling of the backward pass needs
+ * fs_edge2_supported: C1 == 64, C2 == 64, k in {8, 12, 16, 20, 40}.
+ */
+int fs_edge2_supported(int k, int C1, int C2);
+int fs_edge2_fwd(int device, fs_stream_t stream, const float* x, int ldx, const int32_t* idx, int B, int N, int k,
+                 const float* w1, const float* coef1, const float* w2, int C2, const float* gamma2, float* sel,
+                 uint8_t* arg, double* stats, float* gram, float* hsum);
+
 /* ---------------------------------------------------------------- ensemble inference ------- */
 
 /*

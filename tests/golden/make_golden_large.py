@@ -72,6 +72,7 @@ def run(ref_dgcnn, cfg, dynamic, record_graphs=False):
         out["graphs"] = [g.to(torch.int16) for g in graphs]
     else:
         out["static_graph_rowsum"] = model.knn_graph.sum(-1).to(torch.int32)      # (B, N): pins the static graph cheaply
+        out["static_graph"] = model.knn_graph.to(torch.int16)                     # the reference's graph, for teacher forcing
     model.eval()
     with torch.no_grad():
         out["logits_eval"] = model(x).clone()

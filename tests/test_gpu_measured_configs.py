@@ -37,25 +37,65 @@ def _pm_to_bcn(t, B, N):
 
 
 @pytest.mark.parametrize("tag,cfg_key", [("A_static", "config_A"), ("C_static", "config_C")])
-def test_static_end_to_end_at_measured_size(large, lib, tag, cfg_key):
-    """Config A (B=2, N=2048, k=20) and config C (B=1, N=8192, k=40, 9 input channels), static graph, fp32:
-    logits / loss / running statistics / eval logits against the reference's own run at that size."""
+def test_static_end_to_end_at_measured_size(large, lib, tag, cfg_key, monkeypatch):
+    """Config A (B=2, N=2048, k=20) and config C (B=1, N=8192, k=40, 9 input channels), static graph, fp32, against the
+    reference's own run at that size.
+    (1) Free-running: the coordinate graph must equal the oracle's on every non-tie row. On tie rows (the gap between
+        the k-th and the (k+1)-th neighbour is below fp32 rounding: ~1 % of the rows at N=8192, k=40) either neighbour
+        is a correct answer and the reference's own choice depends on its summation order, so the logits of the points
+        that see such a row differ: reported, bounded by the tie-row count.
+    (2) With the reference's graph teacher-forced: logits / loss / gradients / running statistics / eval logits strict."""
     torch.backends.cuda.matmul.allow_tf32 = False
     g, cfg = large[tag], large[cfg_key]
     m, x, y, p = _build(cfg, dynamic=False)
     assert abs(float(x.double().abs().sum()) - g["x_checksum"]) <= 1e-9 * g["x_checksum"]
     m.train()
     logits = m(x.to(DEV))
-    # the static coordinate graph: bit-exact neighbour sets except on tie rows (gap to the first rejected neighbour
-    # within 16 eps of the squared-norm scale), where the reference's own fp32 answer is arbitrary
     rep = compare_knn(m.knn_graph.to(torch.int32), None, x[:, :3], cfg["k"], False, O.knn_with_gap)
-    rows_equal = int((m.knn_graph.sum(-1).to(torch.int32).cpu() == g["static_graph_rowsum"]).sum())
-    print("%s static graph: %s; rows with the reference's index sum: %d of %d" % (tag, rep, rows_equal, cfg["B"] * cfg["N"]))
+    same_as_ref = (m.knn_graph.cpu().sort(-1)[0] == g["static_graph"].long().sort(-1)[0]).all(-1)
+    diff = (logits.detach().cpu() - g["logits"]).abs()
+    frac = float((diff > 1e-4 + 1e-4 * g["logits"].abs()).float().mean())
+    print("%s free-running: graph %s; rows with the reference's neighbour set %d of %d; logits outside rtol 1e-4: %.4f, max %.2e"
+          % (tag, rep, int(same_as_ref.sum()), same_as_ref.numel(), frac, float(diff.max())))
     assert rep["mismatch_non_tie_rows"] == 0, rep
+    # a differing row touches itself and, through three EdgeConv layers, the points around it
+    assert frac <= 60.0 * float((~same_as_ref).float().mean()) + 1e-6
+
+    # (2) teacher-forced: the model computes its static graph with ops.knn_coords; hand it the reference's graph
+    ref_graph = g["static_graph"].to(torch.int32).to(DEV).contiguous()
+    real_knn = ops.knn_coords
+
+    def forced(xc, k, self_loop=False, diag_zero=True, return_dist=False):
+        if (not self_loop) and k == cfg["k"] and not return_dist and tuple(xc.shape[::2]) == tuple(ref_graph.shape[:2]):
+            return ref_graph
+        return real_knn(xc, k, self_loop, diag_zero, return_dist)
+
+    monkeypatch.setattr(ops, "knn_coords", forced)
+    m, x, y, p = _build(cfg, dynamic=False)
+    m.spatial_sort = False                       # the reference's graph is in the caller's point numbering
+    m.train()
+    logits = m(x.to(DEV))
     assert_close(logits, g["logits"], 1e-4, 1e-4, tag + " logits")
     loss = F.cross_entropy(logits, y.to(DEV))
     assert abs(float(loss) - float(g["loss"])) < 1e-4
     loss.backward()
+    # Gradient norms against the reference's (CPU fp32) norms: 5e-3. One quantity is ill-conditioned at B = 2: the
+    # gradient of the global feature is the per-cloud SUM of the BatchNorm input gradient of segmentation.0, and those
+    # sums cancel exactly across the batch (sum_b = 0 in exact arithmetic), so d beta of global_feature is a difference
+    # of rounding-level residues. The yardstick there is the reference module itself in PyTorch eager on this GPU:
+    # at most 3x its own deviation from the CPU run.
+    ref_dev = {}
+    from oracle import reference_shim
+    if reference_shim.available():
+        ref_dgcnn, _, _ = reference_shim.load()
+        rm = ref_dgcnn.DGCNNSeg(k=cfg["k"], in_features=cfg["in_features"], num_classes=cfg["num_classes"], dynamic=False).to(DEV)
+        rm.load_state_dict(p)
+        rm.train()
+        F.cross_entropy(rm(x.to(DEV)), y.to(DEV)).backward()
+        for n, q in rm.named_parameters():
+            r = g["grad_norms"][n]
+            if r >= 1e-9:
+                ref_dev[n] = abs(float(q.grad.double().norm()) - r) / r
     devs = []
     for n, q in m.named_parameters():
         r = g["grad_norms"][n]
@@ -63,8 +103,11 @@ def test_static_end_to_end_at_measured_size(large, lib, tag, cfg_key):
             continue
         devs.append((abs(float(q.grad.double().norm()) - r) / r, n))
     devs.sort(reverse=True)
-    print("%s: largest gradient-norm deviations from the reference: %s" % (tag, [(n, "%.2e" % e) for e, n in devs[:4]]))
-    assert devs[0][0] < 5e-3, devs[:4]
+    print("%s: largest gradient-norm deviations from the reference (CPU): %s" % (tag, [(n, "%.2e" % e) for e, n in devs[:4]]))
+    print("%s: the reference module on this GPU deviates by: %s"
+          % (tag, sorted(((n, "%.2e" % e) for n, e in ref_dev.items()), key=lambda t: -float(t[1]))[:4]))
+    for e, n in devs:
+        assert e < max(5e-3, 3.0 * ref_dev.get(n, 0.0)), (n, e, ref_dev.get(n))
     for n, v in g["running"].items():
         if "num_batches" in n:
             assert int(m.state_dict()[n]) == int(v), n
