@@ -400,3 +400,15 @@ extern "C" int fs_edge3_bwd(int device, fs_stream_t stream_, const float* x, int
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
 }
+
+// The closed-form weight gradient alone (second half of fs_edge3_bwd): for callers that accumulate the per-channel sums
+// and the 64 x 6 moment sums themselves (fs_edge2_bwd).
+extern "C" int fs_edge3_dw(int device, fs_stream_t stream_, const float* acc, const double* dgb, const double* moments,
+                           double count, const float* w, const float* coef, int Cp, int train_stats, float* dw) {
+    if (!acc || !dgb || !w || !coef || !dw || Cp <= 0 || count <= 0) return FS_ERR_BAD_ARG;
+    if (train_stats && !moments) return FS_ERR_BAD_ARG;
+    FS_ENTER(device);
+    edge3_dw_kernel<<<fs_div_up(Cp, 64), 64, 0, (cudaStream_t)stream_>>>(acc, dgb, moments, count, w, coef, Cp, train_stats, dw);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}

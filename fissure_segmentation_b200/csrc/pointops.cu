@@ -61,6 +61,77 @@ fps_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ offset, co
     }
 }
 
+// Register-resident variant for segments of up to FPS_THREADS * PPT points: the segment's coordinates are staged once
+// in shared memory (the winner's coordinates are read from there), every thread keeps its PPT points and their running
+// minimum distances in registers, and one round costs ONE block barrier: each warp publishes its best (distance, index)
+// as a 64-bit key into a buffer selected by the round's parity and every warp reduces the 32 keys redundantly.
+// key = (float bits of the distance << 32) | (0xffffffff - index): the maximum is the farthest point, ties -> lower index.
+template <int PPT>
+__global__ void __launch_bounds__(FPS_THREADS)
+fps_regs_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ offset, const int32_t* __restrict__ new_offset,
+                float* __restrict__ tmp, int32_t* __restrict__ idx) {
+    extern __shared__ float4 s_pts[];
+    __shared__ unsigned long long s_key[2][32];
+    const int s = blockIdx.x;
+    const int start = s == 0 ? 0 : offset[s - 1];
+    const int end = offset[s];
+    const int ostart = s == 0 ? 0 : new_offset[s - 1];
+    const int m = new_offset[s] - ostart;
+    const int n = end - start;
+    if (m <= 0 || n <= 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float px[PPT], py[PPT], pz[PPT], pt[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int j = threadIdx.x + i * FPS_THREADS;
+        px[i] = py[i] = pz[i] = 0.f;
+        pt[i] = -1.f;                                   // slots past the segment never win
+        if (j < n) {
+            px[i] = __ldg(xyz + 3ll * (start + j)); py[i] = __ldg(xyz + 3ll * (start + j) + 1); pz[i] = __ldg(xyz + 3ll * (start + j) + 2);
+            pt[i] = tmp[start + j];
+            s_pts[j] = make_float4(px[i], py[i], pz[i], 0.f);
+        }
+    }
+    if (threadIdx.x == 0) idx[ostart] = start;
+    __syncthreads();
+    int last = 0;
+    for (int r = 1; r < m; ++r) {
+        const float4 lp = s_pts[last];
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int j = threadIdx.x + i * FPS_THREADS;
+            const float dx = px[i] - lp.x, dy = py[i] - lp.y, dz = pz[i] - lp.z;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (pt[i] >= 0.f) {
+                pt[i] = fminf(pt[i], d);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(pt[i]) << 32) | (unsigned)(0xffffffffu - (unsigned)j);
+                best = key > best ? key : best;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(FS_FULL_MASK, best, o);
+            best = ob > best ? ob : best;
+        }
+        if (lane == 0) s_key[r & 1][warp] = best;
+        __syncthreads();
+        best = s_key[r & 1][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(FS_FULL_MASK, best, o);
+            best = ob > best ? ob : best;
+        }
+        last = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
+        if (threadIdx.x == 0) idx[ostart + r] = start + last;
+    }
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {                     // the caller's workspace ends up as the global kernel leaves it
+        const int j = threadIdx.x + i * FPS_THREADS;
+        if (j < n) tmp[start + j] = pt[i];
+    }
+}
+
 __global__ void grouping_fwd_kernel(long long total, int nsample, int c, const float* __restrict__ in,
                                     const int32_t* __restrict__ idx, float* __restrict__ out) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -226,12 +297,29 @@ extern "C" const char* fs_error_string(int code) {
     return "fissure_b200: unknown error";
 }
 
-extern "C" int fs_furthestsampling(int device, fs_stream_t stream_, int b, const float* xyz, const int32_t* offset,
+extern "C" int fs_furthestsampling(int device, fs_stream_t stream_, int b, int n_max, const float* xyz, const int32_t* offset,
                                    const int32_t* new_offset, float* tmp, int32_t* idx) {
     if (!xyz || !offset || !new_offset || !tmp || !idx || b < 0) return FS_ERR_BAD_ARG;
     if (b == 0) return FS_OK;
     FS_ENTER(device);
-    fps_kernel<<<b, FPS_THREADS, 0, (cudaStream_t)stream_>>>(xyz, offset, new_offset, tmp, idx);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // n_max (the largest segment, pointops.py:25-27 computes it for the upstream kernel) selects the register-resident
+    // variant; 0 = unknown -> the global-memory kernel
+    if (n_max > 0 && n_max <= FPS_THREADS * 8) {
+        const size_t smem = (size_t)n_max * sizeof(float4);
+#define FPS_GO(PPT)                                                                                                   \
+    do {                                                                                                              \
+        if (smem > 48 * 1024) FS_CUDA_TRY(cudaFuncSetAttribute(fps_regs_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        fps_regs_kernel<PPT><<<b, FPS_THREADS, smem, stream>>>(xyz, offset, new_offset, tmp, idx);                     \
+    } while (0)
+        if (n_max <= FPS_THREADS) FPS_GO(1);
+        else if (n_max <= 2 * FPS_THREADS) FPS_GO(2);
+        else if (n_max <= 4 * FPS_THREADS) FPS_GO(4);
+        else FPS_GO(8);
+#undef FPS_GO
+    } else {
+        fps_kernel<<<b, FPS_THREADS, 0, stream>>>(xyz, offset, new_offset, tmp, idx);
+    }
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
 }

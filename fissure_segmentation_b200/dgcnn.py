@@ -178,6 +178,13 @@ class EdgeConv(nn.Module):
         C = x_pm.shape[1]
         if (len(self.shared_mlp) > 1 and C == 3 and Cp in (64, 128) and not x_pm.requires_grad
                 and first.norm is not None and first.has_activation and abs(first.negative_slope - 0.2) < 1e-12):
+            last = self.shared_mlp[-1]
+            if (len(self.shared_mlp) == 2 and cdt == torch.bfloat16 and last.norm is not None and last.has_activation
+                    and abs(last.negative_slope - 0.2) < 1e-12 and last.norm.training == first.norm.training
+                    and ops.edge2_supported(graph.k, Cp, last.conv.out_channels)):
+                # both layers in one tcgen05 kernel each way: no edge tensor is written (csrc/edge2.cu); bf16 operands,
+                # like the cuBLAS product of the materialised path in this precision mode
+                return ops.edgeconv2_fused(x_pm.float().contiguous(), first, last, graph)
             # first layer on raw coordinates: batch statistics from the moments of the 6-D edge vectors, H written
             # once, weight gradient accumulated straight from dH (csrc/edge3.cu)
             h = ops.edge_first3(x_pm.float().contiguous(), first.conv.weight, first.norm, graph, cdt)

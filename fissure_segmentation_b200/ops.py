@@ -682,3 +682,87 @@ def edge_first3(x, conv_weight, bn, graph, out_dtype):
     assert x.dtype == torch.float32 and x.stride(1) == 1
     return _EdgeFirst3Fn.apply(x, conv_weight, bn.weight, bn.bias, graph, bn.running_mean, bn.running_var,
                                bn.num_batches_tracked, bn.training, bn.eps, bn.momentum, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------- fused two-layer EdgeConv
+
+USE_FUSED_EDGE2 = os.environ.get("FS_EDGE2", "1") != "0"
+
+
+def edge2_supported(k, C1, C2):
+    return bool(USE_FUSED_EDGE2 and _lib.load().fs_edge2_supported(int(k), int(C1), int(C2)))
+
+
+class _EdgeConv2Fn(torch.autograd.Function):
+    """out_i = LeakyReLU(BN2(max_j W2 LeakyReLU(BN1(W1 [x_j - x_i, x_i])))) for 3-channel coordinates x: the two-layer
+    EdgeConv of models/dgcnn.py:119, 237-241 in two kernels forward / backward that never write an edge tensor
+    (csrc/edge2.cu). bf16 tensor-core operands, fp32 accumulation."""
+
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, graph, rm1, rv1, nbt1, rm2, rv2, nbt2, training, eps, momentum):
+        B, N, k = graph.B, graph.N, graph.k
+        P = B * N
+        dev = x.device
+        C1, C2 = w1.shape[0], w2.shape[0]
+        w1m = w1.detach().reshape(C1, 6).float().contiguous()
+        w2m = w2.detach().reshape(C2, C1).float().contiguous()
+        g1f, b1f, g2f, b2f = (t.detach().float() for t in (g1, b1, g2, b2))
+        coef1 = torch.empty(4 * C1, dtype=torch.float32, device=dev)
+        mom = None
+        if training:
+            mom = _zeros64(_lib.load().fs_edge3_moment_doubles(), dev)
+            _lib.call("fs_edge3_bn_coef", x, x, x.stride(0), graph.idx, B, N, k, w1m, C1, g1f, b1f, eps, momentum, mom, coef1,
+                      rm1, rv1, nbt1)
+        else:
+            _lib.call("fs_bn_coef_eval", x, C1, g1f, b1f, rm1, rv1, eps, coef1)
+        sel = torch.empty(P, C2, dtype=torch.float32, device=dev)
+        arg = torch.empty(P, C2, dtype=torch.uint8, device=dev)
+        stats = gram = hsum = None
+        if training:
+            stats = _stats_buffer(C2, dev)
+            gh = _zeros64((C1 * C1 + C1 + 1) // 2 + 1, dev).view(torch.float32)
+            gram, hsum = gh[:C1 * C1].view(C1, C1), gh[C1 * C1:C1 * C1 + C1]
+        _lib.call("fs_edge2_fwd", x, x, x.stride(0), graph.idx, B, N, k, w1m, coef1, w2m, C2, g2f, sel, arg, stats, gram, hsum)
+        coef2 = _bn_coef(x, stats, P * k, g2f, b2f, rm2, rv2, nbt2, training, C2, eps, momentum)
+        out = torch.empty(P, C2, dtype=torch.float32, device=dev)
+        _lib.call("fs_edgeconv_apply", x, sel, None, 0, 0, P, C2, coef2, out, _lib.dtype_code(out), out.stride(0))
+        ctx.graph, ctx.training = graph, training
+        ctx.shapes = (w1.shape, w2.shape)
+        ctx.save_for_backward(x, w1m, w2m, coef1, coef2, sel, arg, mom, gram, hsum)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w1m, w2m, coef1, coef2, sel, arg, mom, gram, hsum = ctx.saved_tensors
+        graph = ctx.graph
+        B, N, k = graph.B, graph.N, graph.k
+        P = B * N
+        C1, C2 = w1m.shape[0], w2m.shape[0]
+        dev = x.device
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        d = torch.empty(P, C2, dtype=torch.float32, device=dev)
+        dgb2 = _stats_buffer(C2, dev)
+        _lib.call("fs_edgeconv_bwd_reduce", x, g, _lib.dtype_code(g), g.stride(0), sel, None, 0, 0, P, C2, coef2, d, dgb2)
+        dgb1 = _stats_buffer(C1, dev)
+        nscr = _lib.load().fs_edge2_bwd_scratch_floats()
+        scratch = _zeros64((nscr + C1 * 6 + 1) // 2 + 1, dev).view(torch.float32)
+        acc1 = scratch[nscr:nscr + C1 * 6]
+        dw2 = torch.empty(C2, C1, dtype=torch.float32, device=dev)
+        _lib.call("fs_edge2_bwd", x, x, x.stride(0), graph.idx, B, N, k, w1m, coef1, w2m, C2, coef2, dgb2, int(ctx.training),
+                  gram, hsum, d, arg, scratch, dgb1, acc1, dw2)
+        dw1 = torch.empty(C1, 6, dtype=torch.float32, device=dev)
+        _lib.call("fs_edge3_dw", x, acc1, dgb1, mom, float(P * k), w1m, coef1, C1, int(ctx.training), dw1)
+        dgb1f, dgb2f = dgb1[:2 * C1].float(), dgb2[:2 * C2].float()
+        return (None, dw1.view(ctx.shapes[0]), dgb1f[C1:], dgb1f[:C1], dw2.view(ctx.shapes[1]), dgb2f[C2:], dgb2f[:C2],
+                None, None, None, None, None, None, None, None, None, None)
+
+
+def edgeconv2_fused(x, layer1, layer2, graph):
+    """x (P, >=3) fp32 point-major coordinates; layer1 / layer2: the two SharedFullyConnected blocks of the EdgeConv."""
+    bn1, bn2 = layer1.norm, layer2.norm
+    return _EdgeConv2Fn.apply(x, layer1.conv.weight, bn1.weight, bn1.bias, layer2.conv.weight, bn2.weight, bn2.bias, graph,
+                              bn1.running_mean, bn1.running_var, bn1.num_batches_tracked, bn2.running_mean, bn2.running_var,
+                              bn2.num_batches_tracked, bn1.training, bn1.eps, bn1.momentum)

@@ -23,7 +23,8 @@ def _i32(t):
 
 
 def furthestsampling_cuda(b, n_max, xyz, offset, new_offset, tmp, idx):  # pointops.py:35
-    _lib.call("fs_furthestsampling", xyz, int(b), _f32(xyz), _i32(offset), _i32(new_offset), _f32(tmp), _i32(idx))
+    _lib.call("fs_furthestsampling", xyz, int(b), int(n_max), _f32(xyz), _i32(offset), _i32(new_offset), _f32(tmp),
+              _i32(idx))
 
 
 # Per-level kNN cache. The reference's PointTransformerLayer issues the SAME query twice in a row

@@ -125,8 +125,11 @@ int fs_knnquery(int device, fs_stream_t stream, int m, int nsample, const float*
  * Farthest point sampling per segment. Replaces pointops_cuda.furthestsampling_cuda at
  * models/pointtransformer/pointops.py:35. `tmp` [n] must be pre-filled with 1e10 by the caller
  * (pointops.py:32); idx [m_total] receives global row indices, first pick = segment start.
+ * n_max = size of the largest segment (the second argument of the upstream call, pointops.py:25-27, 35); when
+ * 0 < n_max <= 8192 every thread keeps its points and running distances in registers and the segment's coordinates
+ * sit in shared memory (one block barrier per pick); n_max = 0 selects the global-memory kernel.
  */
-int fs_furthestsampling(int device, fs_stream_t stream, int b, const float* xyz,
+int fs_furthestsampling(int device, fs_stream_t stream, int b, int n_max, const float* xyz,
                         const int32_t* offset, const int32_t* new_offset, float* tmp, int32_t* idx);
 
 /*
@@ -382,15 +385,36 @@ int fs_adam_step(int device, fs_stream_t stream, float* param, const float* grad
  * per-thread reduction.
  *   w1 [64,6], coef1 [4*64] (mu | 1/sigma | gamma/sigma | beta), w2 [C2,64] fp32, gamma2 [C2] (sign selects max / min)
  *   sel [P,C2] fp32 selected pre-activation, arg [P,C2] uint8 slot of the selected edge
- *   stats (nullable = eval): fs_stats_buffer_doubles(C2) doubles, zero-filled: sum z, sum z^2 over all P*k edges
- *   gram [64*64], hsum [64] (required with stats, zero-filled): sum_e h_e h_e^T and sum_e h_e (bf16-rounded h), which
- *   the BatchNorm coupling of the backward pass needs
+ *   stats (nullable = eval): fs_stats_buffer_doubles(C2) doubles: receives sum z, sum z^2 over all P*k edges, derived
+ *   from gram [64*64] = sum_e h_e h_e^T (accumulated on the tensor cores) and hsum [64] = sum_e h_e (both required with
+ *   stats, zero-filled), which the BatchNorm coupling of the backward pass needs as well
  * fs_edge2_supported: C1 == 64, C2 == 64, k in {8, 12, 16, 20, 40}.
  */
 int fs_edge2_supported(int k, int C1, int C2);
 int fs_edge2_fwd(int device, fs_stream_t stream, const float* x, int ldx, const int32_t* idx, int B, int N, int k,
                  const float* w1, const float* coef1, const float* w2, int C2, const float* gamma2, float* sel,
                  uint8_t* arg, double* stats, float* gram, float* hsum);
+/*
+ * Backward of fs_edge2_fwd: dz_e = R_e + alpha + beta' (.) z_e (routed gradient + BatchNorm-2 coupling) gives
+ *   dh_e = [W2^T | Gm] [R_e ; h_e] + a0     (one tcgen05 product per tile, Gm = W2^T diag(beta') W2, a0 = W2^T alpha)
+ * with H recomputed from the coordinates; the epilogue applies LeakyReLU' of layer 1 and accumulates the sums
+ * fs_edge3_bwd takes from a materialised dH; sum_e R_e h_e^T accumulates on the tensor cores (MN-major operands).
+ * Three launches: coupling coefficients (one CTA), the tile kernel, dW2 = R^T H + alpha hsum^T + diag(beta') W2 S.
+ *   coef2 [4*64] BatchNorm-2 coefficients (mu | 1/sigma | gamma/sigma | beta), dgb2 = statistics buffer of
+ *   fs_edgeconv_bwd_reduce (sum d | sum d zhat), train_stats = 1 in training mode, gram / hsum from the forward,
+ *   d2 [P,64] = upstream gradient times LeakyReLU' of layer 2, arg [P,64]
+ *   scratch: fs_edge2_bwd_scratch_floats() floats, zero-filled
+ *   outputs: dgb1 (fs_stats_buffer_doubles(64), zero-filled: sum t | sum t * yhat of layer 1), acc1 [64,6] zero-filled
+ *   (sum t (x) e, input of fs_edge3_dw), dw2 [64,64]
+ */
+size_t fs_edge2_bwd_scratch_floats(void);
+int fs_edge2_bwd(int device, fs_stream_t stream, const float* x, int ldx, const int32_t* idx, int B, int N, int k,
+                 const float* w1, const float* coef1, const float* w2, int C2, const float* coef2, const double* dgb2,
+                 int train_stats, const float* gram, const float* hsum, const float* d2, const uint8_t* arg,
+                 float* scratch, double* dgb1, float* acc1, float* dw2);
+/* dW1 [Cp,6] from the sums of a layer-1 backward pass (the closed-form BatchNorm coupling of fs_edge3_bwd). */
+int fs_edge3_dw(int device, fs_stream_t stream, const float* acc, const double* dgb, const double* moments,
+                double count, const float* w, const float* coef, int Cp, int train_stats, float* dw);
 
 /* ---------------------------------------------------------------- ensemble inference ------- */
 

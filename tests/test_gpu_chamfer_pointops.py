@@ -87,6 +87,21 @@ def test_furthestsampling_matches_restatement(lib):
     assert np.array_equal(idx.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("sizes,n_max", [([5000, 300], 5000), ([5000, 300], 0), ([9000], 9000), ([1024, 1023, 1025], 1025)])
+def test_furthestsampling_variants_agree(lib, sizes, n_max):
+    """Register-resident kernel (n_max <= 8192: 1, 2, 4 or 8 points per thread) and the global-memory kernel
+    (n_max = 0 or larger segments) pick the same points as the restatement of the upstream operator."""
+    new_sizes = [max(1, sz // 4) for sz in sizes]
+    gen = torch.Generator().manual_seed(7)
+    xyz = torch.rand(sum(sizes), 3, generator=gen)
+    off, noff = _segments(sizes), _segments(new_sizes)
+    idx = torch.zeros(sum(new_sizes), dtype=torch.int32, device=DEV)
+    tmp = torch.full((sum(sizes),), 1e10, device=DEV)
+    pointops_cuda.furthestsampling_cuda(len(sizes), n_max, xyz.to(DEV), off.to(DEV), noff.to(DEV), tmp, idx)
+    ref = pointops_oracle.furthestsampling(xyz.numpy(), off.tolist(), noff.tolist())
+    assert np.array_equal(idx.cpu().numpy(), ref)
+
+
 def test_grouping_interpolation_subtraction_aggregation(lib):
     gen = torch.Generator().manual_seed(3)
     n, m, ns, c, wc = 200, 150, 8, 16, 4
