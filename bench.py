@@ -317,7 +317,11 @@ def entry_rooflines(args, timed_ms, hbm_peak, tensor_peak, fma_peak, peak_kind):
         "fs_knn_feat_tc": ("tensor", 2.0 * B * N * N * 64, tensor_peak, "TFLOP/s",
                            "fs_knn_feat_tc entry point (operand prep + knn_tc_select [tcgen05] + finalize), C=64"),
         # 3-D kNN: (2C+2) = 8 flops per pair, against the measured FP32 FMA rate
-        "fs_knn3d": ("fp32_fma", 8.0 * B * N * N, fma_peak, "TFLOP/s", "fs_knn3d (coordinate kNN, C=3)"),
+        "fs_knn3d": ("fp32_fma", 8.0 * B * N * N, fma_peak, "TFLOP/s", "fs_knn3d (coordinate kNN, C=3, SIMT)"),
+        # the same through the tensor-core kernels: the distances come out of ONE K = 16 tcgen05 step (hi/lo split of the
+        # three coordinates + norms), the CUDA cores only select; reported against the FP32 FMA rate of the SIMT form
+        "fs_knn3d_tc": ("fp32_fma", 8.0 * B * N * N, fma_peak, "TFLOP/s",
+                        "fs_knn3d_tc entry point (coordinate kNN, C=3: operand prep + knn_tc_select [tcgen05] + finalize)"),
         # EdgeConv gather/max pass, fp32 table: [a|b] 2*Cp*4 + idx 4k + sel 4Cp + arg Cp + sum_y 4Cp bytes per point
         "fs_edgeconv_gather": ("hbm", float(P) * (2 * cp * 4 + 4 * k + 4 * cp + cp + 4 * cp), hbm_peak, "GB/s",
                                "fs_edgeconv_gather (ec2/ec3 gather/max pass, Cp=64, train)"),
@@ -478,7 +482,7 @@ def run_train(args):
 
     # ---- per-call duration of the roofline entry points: CUDA events around their calls in 3 eager steps of the same
     #      workload (events cannot be read back from inside a replayed graph)
-    timed_names = {"fs_edgeconv_gather", "fs_knn_feat_tc", "fs_knn3d", "fs_edge2_fwd", "fs_edge2_bwd"}
+    timed_names = {"fs_edgeconv_gather", "fs_knn_feat_tc", "fs_knn3d", "fs_knn3d_tc", "fs_edge2_fwd", "fs_edge2_bwd"}
     _lib.time_calls.update(timed_names)
     _lib.timed.clear()
     for i in range(3):
@@ -500,7 +504,7 @@ def run_train(args):
         roofs = entry_rooflines(args, timed_ms, hbm_peak, tensor_peak, fma_peak, peak_kind)
         prof = {"fs_knn_feat_tc": from_profile("knn_tc_select"), "fs_edgeconv_gather": from_profile("edgeconv_gather"),
                 "fs_edge2_fwd": from_profile("edge2_fwd"), "fs_edge2_bwd": from_profile("edge2_bwd"),
-                "fs_knn3d": from_profile("knn3d")}
+                "fs_knn3d": from_profile("knn3d"), "fs_knn3d_tc": from_profile("knn_tc_select")}
         for name, r in roofs.items():
             p = prof.get(name)
             if p is not None:

@@ -58,8 +58,11 @@ def test_static_end_to_end_at_measured_size(large, lib, tag, cfg_key, monkeypatc
     print("%s free-running: graph %s; rows with the reference's neighbour set %d of %d; logits outside rtol 1e-4: %.4f, max %.2e"
           % (tag, rep, int(same_as_ref.sum()), same_as_ref.numel(), frac, float(diff.max())))
     assert rep["mismatch_non_tie_rows"] == 0, rep
-    # a differing row touches itself and, through three EdgeConv layers, the points around it
-    assert frac <= 60.0 * float((~same_as_ref).float().mean()) + 1e-6
+    # A tie row is broken by index, and the model numbers the points along the Morton curve (spatial_sort), the
+    # reference in the caller's order: on tie rows the two may keep different (equally near) neighbours, and each such
+    # row reaches the points around it through three EdgeConv layers. Measured: 1.9 % of the logits at 1.3 % tie rows
+    # (config C), 0 at config A. Bound: 5x the tie-row fraction.
+    assert frac <= 5.0 * rep["tie_rows"] / rep["rows"] + 1e-3, (frac, rep)
 
     # (2) teacher-forced: the model computes its static graph with ops.knn_coords; hand it the reference's graph
     ref_graph = g["static_graph"].to(torch.int32).to(DEV).contiguous()
@@ -234,8 +237,11 @@ def test_bench_shape_batch32_slice_against_oracle(lib):
     assert report["channels"].count(64) == 4 and report["channels"].count(3) == 2      # every graph on the tcgen05 path
     assert report["redo_rows"] <= 0.01 * report["rows"]
     # eval mode, fp32: per-cloud independent -> the 2-cloud slice of a B=32 forward equals the oracle on 2 clouds
+    # The bench clouds sit on the voxel lattice: exact distance ties are common and are broken by index, so the
+    # comparison keeps the caller's point numbering on both sides (spatial_sort off; the sorted path is covered by
+    # the kNN parity tests and by the free-running checks above).
     m.precision = "fp32"
-    m.spatial_sort = True
+    m.spatial_sort = False
     m.eval()
     with torch.no_grad():
         ev = m(x.to(DEV))[sl].cpu()
@@ -387,14 +393,15 @@ def test_auto_precision_follows_autocast(lib):
 
 def test_cuda_graph_replay_equals_eager_step(lib):
     """bench.py captures the whole training step in a CUDA graph: two replays on the same input must reproduce the
-    eager step (same kernels, same arena memset) up to the summation order of the atomics (fp64 batch statistics,
-    fp32 routed scatter)."""
+    eager step (same kernels, same arena memset). fp32 mode and a static graph, so that the only run-to-run variation
+    is the summation order of the atomics (fp64 batch statistics, fp32 routed scatter); with dynamic graphs and bf16
+    tiles a 1e-7 difference can flip a near-tie neighbour or a bf16 rounding and move single logits by 1e-2."""
     torch.manual_seed(0)
     B, N, k = 4, 2048, 20
-    x, y = synth.make_batch(B, N, seed=77)
+    x, y = synth.make_batch(B, N, seed=77, jitter=True)
     xd, yd = x.to(DEV), y.to(DEV)
-    m = fs.DGCNNSeg(k=k, in_features=3, num_classes=4).to(DEV).train()
-    m.precision = "bf16"
+    m = fs.DGCNNSeg(k=k, in_features=3, num_classes=4, dynamic=False).to(DEV).train()
+    m.precision = "fp32"
     for q in m.modules():
         if isinstance(q, torch.nn.modules.batchnorm._BatchNorm):
             q.momentum = 0.0                              # running statistics frozen: every step sees the same state
@@ -424,6 +431,5 @@ def test_cuda_graph_replay_equals_eager_step(lib):
         out_static.zero_()
         graph.replay()
         torch.cuda.synchronize()
-        # fp64 atomics of the batch statistics may round differently from run to run (1e-16): allow rounding noise
-        assert float((out_static - eager_out).abs().max()) < 1e-3
-        assert float((gw - eager_gw).norm() / eager_gw.norm()) < 1e-3
+        assert float((out_static - eager_out).abs().max()) < 1e-4
+        assert float((gw - eager_gw).norm() / eager_gw.norm()) < 1e-4
