@@ -45,7 +45,7 @@ constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr int TC_STAGE_BYTES = 32 * 32 * 4;     // per-warp staging of one 32 x 32 score block
 constexpr int TC_CAP = 128;          // survivor slots per query, TC_CAP / 2 per column half
 constexpr int TC_MAX_KK = 64;        // 64 class minima per row
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_ACC = 4;
 constexpr int TC_EXTRAS = 6;         // extras halfs: A = [1, 1, n_h, n_l, -T_h, -T_l], B = [n_h, n_l, 1, 1, 1, 1]
 
@@ -88,7 +88,7 @@ bool tc_make_shape(int C, TcShape* out) {
     s.tmem_cols = C == 256 ? 512 : 256;
     s.nacc = (s.tmem_cols - s.acc0) / TC_NB;
     if (s.nacc > TC_MAX_ACC) s.nacc = TC_MAX_ACC;
-    s.stages = C <= 64 ? 4 : 3;
+    s.stages = C == 3 ? 8 : (C == 64 ? 4 : 3);      // 8 / 16 / 24 / 40 KB per stage
     *out = s;
     return true;
 }
@@ -454,15 +454,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __grid_constant__ CUtensorMap map_b,
                      int N, int kk, int diag_zero, const TcShape sh, const float* __restrict__ cnorm,
                      const float* __restrict__ sqnorm, const float* __restrict__ stats, int32_t* __restrict__ cand_j,
-                     float* __restrict__ cand_d, int32_t* __restrict__ cand_n, float* __restrict__ row_T, long long* __restrict__ tl) {
+                     float* __restrict__ cand_d, int32_t* __restrict__ cand_n, float* __restrict__ row_T) {
     extern __shared__ uint8_t smem_raw[];
-#define TL(i) do { if (tl && (threadIdx.x & 31) == 0) tl[((long long)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (threadIdx.x >> 5)) * 8 + (i)] = clock64(); } while (0)
-    TL(0);
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_b = smem;
     const int stage_bytes = sh.nboxes * TC_BOX_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + sh.stages * stage_bytes);
-    // bars: b_full[4] | b_empty[4] | acc_full[4] | acc_empty[4] | a_full | a2_full
+    // bars: b_full[8] | b_empty[8] | acc_full[4] | acc_empty[4] | a_full | a2_full
     uint64_t* b_full = bars;
     uint64_t* b_empty = bars + TC_MAX_STAGES;
     uint64_t* acc_full = bars + 2 * TC_MAX_STAGES;
@@ -497,7 +495,6 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    TL(1);
 
     if (warp == TC_WARP_TMA) {
         // ===================== TMA producer =====================
@@ -577,7 +574,6 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(a_full));
         }
-        TL(2);
         float* stage = stage_all + warp * (TC_STAGE_BYTES / 4) + lane * 32;   // this thread's 32 staged scores
         float gm[32];
 #pragma unroll
@@ -590,7 +586,6 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
         uint32_t ph = 0;
         for (int it = 0; it < 2 * T; ++it) {
             if (it == T) {
-                TL(3);
                 // between the sweeps: the two column halves of a row hold 32 class minima each over DISJOINT candidate
                 // sets = 64 classes. Each thread sorts its own 32, the pair exchanges them through the staging blocks
                 // (named barrier per warp pair); min / max(own[i], other[31-i]) is the (bitonic) lower / upper half of the
@@ -658,7 +653,6 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(a2_full));
                 }
-                TL(4);
             }
             mbar_wait(smem_u32(acc_full + a), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -713,7 +707,6 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
             if (it == T - 1) jb = cb * 32;
         }
         if (row_ok) cand_n[(cloud0 + qrow) * TC_HALVES + cb] = cnt;
-        TL(5);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -724,8 +717,6 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
         else
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
     }
-    TL(6);
-#undef TL
 }
 
 // ----------------------------------------------------------------------------------------------- finalize
@@ -952,7 +943,6 @@ int get_encode_fn(EncodeTiledFn* out) {
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-long long* g_tc_timeline = nullptr;     // development only (fs_tc_set_timeline): per-CTA phase timestamps
 
 struct TcWorkspace {
     __half* A; __half* Bm; int32_t* cand_j; float* cand_d; int32_t* cand_n; float* sqnorm; float* cnorm; float* row_T;
@@ -1006,7 +996,7 @@ int tc_run(cudaStream_t stream, const TcShape& sh, const TcWorkspace& w, const f
     FS_CUDA_TRY(cudaFuncSetAttribute(knn_tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(fs_div_up(N, TC_M), B);
     knn_tc_select_kernel<<<grid, TC_THREADS, smem, stream>>>(w.A, P, map_b, N, kk, diag_zero, sh, w.cnorm, w.sqnorm, w.stats,
-                                                              w.cand_j, w.cand_d, w.cand_n, w.row_T, g_tc_timeline);
+                                                              w.cand_j, w.cand_d, w.cand_n, w.row_T);
     FS_RETURN_IF_LAUNCH_FAILED();
     knn_tc_finalize_kernel<XYZ><<<fs_div_up(P, 8), 256, 0, stream>>>(x, ldx, w.xyz_pm, N, P, k, self_loop, diag_zero, sh, w.cand_j,
                                                                      w.cand_d, w.cand_n, w.row_T, w.sqnorm, w.cnorm, w.stats,
@@ -1111,7 +1101,3 @@ extern "C" int fs_knn3d_tc(int device, fs_stream_t stream_, const float* coords,
     return fs_knn_feat_masked(stream, reinterpret_cast<const float*>(w.xyz_pm), 4, B, N, 3, k, self_loop, diag_zero, idx, nullptr,
                               w.sqnorm, w.redo);
 }
-
-// Development hook: device buffer of (CTAs * 16 warps * 8) long long that receives clock64() at the phases of
-// knn_tc_select_kernel (null = off). Not part of the public contract (not declared in include/fissure_b200.h).
-extern "C" void fs_tc_set_timeline(long long* buf) { g_tc_timeline = buf; }
