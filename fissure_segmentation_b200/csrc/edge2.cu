@@ -290,7 +290,10 @@ edge2_fwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int item = tid + i * E2_PROD_THREADS;
-                if (item < Cfg::UNIT_PTS * 16) *reinterpret_cast<float4*>(b_s + (item >> 4) * E2_C + (item & 15) * 4) = pre.base[i];
+                // item = (point, channel quad q): chunk = q / 2, half = q % 2 -> [point][half][chunk][4], so that the two
+                // 128-bit reads of a chunk are bank-conflict-free across the eight chunk lanes of a warp
+                if (item < Cfg::UNIT_PTS * 16)
+                    *reinterpret_cast<float4*>(b_s + (item >> 4) * E2_C + (item & 1) * 32 + ((item & 15) >> 1) * 4) = pre.base[i];
             }
             asm volatile("bar.sync 1, %0;" ::"n"(E2_PROD_THREADS) : "memory");
             if (u + gridDim.x < n_units) e2_prefetch<K>(pre, x, ldx, idx, P, N, (u + gridDim.x) * Cfg::UNIT_PTS, par, tid);
@@ -299,9 +302,9 @@ edge2_fwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict
             for (int E = el; E < Cfg::UNIT_EDGES; E += E2_EDGE_LANES) {
                 const int g = E / NE, e = E - g * NE;
                 const int pl = e / K;
-                const float* bp = b_s + (g * PP + pl) * E2_C + chunk * 8;
+                const float* bp = b_s + (g * PP + pl) * E2_C + chunk * 4;
                 const uint4 v = e2_hidden_chunk(W, d_s[E], *reinterpret_cast<const float4*>(bp),
-                                                *reinterpret_cast<const float4*>(bp + 4), TRAIN ? hs : nullptr);
+                                                *reinterpret_cast<const float4*>(bp + 32), TRAIN ? hs : nullptr);
                 *reinterpret_cast<uint4*>(h_s + g * Cfg::H_ATOM + sw128_offset(e, chunk)) = v;
             }
             fence_proxy_async_smem();
@@ -619,7 +622,7 @@ edge2_bwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict
             for (int i = 0; i < 2; ++i) {
                 const int item = tid + i * E2_PROD_THREADS;
                 if (item < Cfg::UNIT_PTS * 16) {
-                    *reinterpret_cast<float4*>(b_s + (item >> 4) * E2_C + (item & 15) * 4) = pre.base[i];
+                    *reinterpret_cast<float4*>(b_s + (item >> 4) * E2_C + (item & 1) * 32 + ((item & 15) >> 1) * 4) = pre.base[i];   // [pt][half][chunk][4]
                     *reinterpret_cast<float4*>(y_s + (item >> 4) * E2_C + (item & 15) * 4) = preb.basey[i];
                 }
             }
@@ -657,9 +660,9 @@ edge2_bwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict
             for (int E = el; E < Cfg::UNIT_EDGES; E += E2_EDGE_LANES) {
                 const int g = E / NE, e = E - g * NE;
                 const int pl = e / K;
-                const float* bp = b_s + (g * PP + pl) * E2_C + chunk * 8;
+                const float* bp = b_s + (g * PP + pl) * E2_C + chunk * 4;
                 const uint4 v = e2_hidden_chunk(W, d_s[E], *reinterpret_cast<const float4*>(bp),
-                                                *reinterpret_cast<const float4*>(bp + 4), nullptr);
+                                                *reinterpret_cast<const float4*>(bp + 32), nullptr);
                 *reinterpret_cast<uint4*>(tiles + (2 * g + 1) * BC::T_ATOM + sw128_offset(e, chunk)) = v;
             }
             fence_proxy_async_smem();

@@ -245,11 +245,20 @@ def test_bench_shape_batch32_slice_against_oracle(lib):
     m.eval()
     with torch.no_grad():
         ev = m(x.to(DEV))[sl].cpu()
-        ref = O.dgcnn_seg({n: v.detach().cpu().clone() for n, v in m.state_dict().items()}, xs, k, dynamic=True, training=False)
+        # the graphs of the eval forward (same kernels, same numbering), handed to the oracle: on the lattice a tie row
+        # may legitimately keep another equally near neighbour, which would otherwise spread through three layers
+        e1 = m.ec1.build_graph(x_pm, B, N)
+        y1 = m.ec1.forward_pm(x_pm, B, N, e1)
+        e2 = m.ec2.build_graph(y1, B, N)
+        y2 = m.ec2.forward_pm(y1, B, N, e2)
+        e3 = m.ec3.build_graph(y2, B, N)
+        gs = [t.idx[sl].cpu().long() for t in (e1, e2, e3)]
+        sd = {n: v.detach().cpu().clone() for n, v in m.state_dict().items()}
+        ref = O.dgcnn_seg(sd, xs, k, dynamic=True, training=False, fixed_graphs=gs)
     diff = (ev - ref).abs()
     frac = float((diff > 1e-4 + 1e-4 * ref.abs()).float().mean())
     print("bench shape eval slice: max |dlogit| %.3e, fraction outside rtol 1e-4: %.5f" % (float(diff.max()), frac))
-    assert frac < 0.02 and float(diff.max()) < 0.5      # dynamic: a flipped near-tie moves single points (reported)
+    assert frac == 0.0 and float(diff.max()) < 1e-3
 
 
 def test_tensor_core_knn_hostile_inputs(lib):
