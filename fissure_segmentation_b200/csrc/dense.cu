@@ -269,7 +269,7 @@ __device__ __forceinline__ float from_ordered_u32(unsigned int u) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(DN_THREADS)
+__global__ void __launch_bounds__(DN_THREADS, 3)
 pool_reduce_kernel(const T* __restrict__ x, int ld, int N, int C, const float* __restrict__ gamma,
                    unsigned long long* __restrict__ packed, double* __restrict__ stats) {
     constexpr int V = Vec<T>::N;
@@ -493,7 +493,9 @@ extern "C" int fs_pool_reduce(int device, fs_stream_t stream_, const void* x, in
     if (!pow2_width(C, vec)) return FS_ERR_UNSUPPORTED;
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
-    int chunks = (4 * FS_NUM_SMS + B - 1) / B;          // about four blocks per SM in total
+    // three blocks are resident per SM (__launch_bounds__): the grid is at most ONE full wave - a grid of 2.05 waves
+    // (the first sizing) spent half of its time in a nearly empty third wave
+    int chunks = (3 * FS_NUM_SMS) / B;
     const int rpp = rows_per_pass(C, vec);
     if (chunks > (N + 4 * rpp - 1) / (4 * rpp)) chunks = (N + 4 * rpp - 1) / (4 * rpp);
     if (chunks < 1) chunks = 1;

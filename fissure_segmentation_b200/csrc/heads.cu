@@ -1,0 +1,593 @@
+// Backward of the pooled global-feature layer without the dense (B*N x C_out) gradient, and the feature-table glue.
+//
+// Layer (models/dgcnn.py:123-126, 156): y = X W^T (P x C, P = B*N rows, K input channels), z = BN(y), out[b, c] =
+// max_r LeakyReLU(z). The gradient of y is   dy[r, c] = S[r, c] + a_c + b_c y[r, c]   where S has ONE non-zero per
+// (cloud, channel) - the arg-max row - and a, b come from the two BatchNorm reductions (which only need the B x C
+// selected values). With y = X W^T the dense part collapses onto K x K matrices:
+//     dX = S W + 1 (a^T W) + X (W^T diag(b) W)                  one P x K x K GEMM instead of P x C x K
+//     dW = S^T X + a colsum(X)^T + diag(b) W (X^T X)            one K x P x K Gram instead of C x P x K
+// so the P x C gradient (134 MB at P = 65536, C = 1024) is neither written nor read and y is not kept for backward.
+// The GEMMs stay library calls (host side, ops.py); the kernels here are the sparse parts and the coefficient vectors.
+#include "fs_common.cuh"
+
+namespace {
+
+// a_c, b_c and the routed, scaled gradient sp[b, c] = scale_c * g[b, c] * LeakyReLU'(z_sel[b, c]).
+// coef = [mean | inv_std | scale = gamma * inv_std | beta] (fs_bn_finalize layout), dgb = [dbeta | dgamma] (double).
+__global__ void pool_lin_prep_kernel(const float* __restrict__ g, const float* __restrict__ sel, const float* __restrict__ coef,
+                                     float slope, const double* __restrict__ dgb, double count, int train_stats, int B, int C,
+                                     float* __restrict__ a, float* __restrict__ bvec, float* __restrict__ sp) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)B * C) return;
+    const int c = (int)(e % C);
+    const float mu = __ldg(coef + c), sc = __ldg(coef + 2 * C + c);
+    const float zs = fmaf(sc, __ldg(sel + e) - mu, __ldg(coef + 3 * C + c));
+    const float gv = __ldg(g + e);
+    sp[e] = sc * (zs > 0.f ? gv : slope * gv);
+    if (e < C) {
+        const float mb = train_stats ? (float)(dgb[c] / count) : 0.f;
+        const float mg = train_stats ? (float)(dgb[C + c] / count) * __ldg(coef + C + c) : 0.f;
+        a[c] = sc * (mg * mu - mb);
+        bvec[c] = -sc * mg;
+    }
+}
+
+template <typename T> __device__ __forceinline__ float ld_as_float(const T* p);
+template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void st_from_float(T* p, float v);
+template <> __device__ __forceinline__ void st_from_float<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 16-byte chunk of a row: 8 bf16 or 4 fp32 values
+template <typename T> struct Chunk;
+template <> struct Chunk<__nv_bfloat16> {
+    static constexpr int N = 8;
+    __device__ __forceinline__ static void decode(const uint4& r, float* f) { fs_bf16x8_to_float(r, f); }
+    __device__ __forceinline__ static void red_add(__nv_bfloat16* p, const float* f) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<__nv_bfloat162*>(p) + i, __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]));
+    }
+    __device__ __forceinline__ static void load(const __nv_bfloat16* p, float* f) { fs_bf16x8_to_float(*reinterpret_cast<const uint4*>(p), f); }
+    __device__ __forceinline__ static void store(__nv_bfloat16* p, const float* f) {
+        uint4 v;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = v;
+    }
+};
+template <> struct Chunk<float> {
+    static constexpr int N = 4;
+    __device__ __forceinline__ static void decode(const uint4& r, float* f) {
+        f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y); f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+    }
+    // fire-and-forget add (RED): the caller guarantees ONE add per element, so the result does not depend on any order
+    __device__ __forceinline__ static void red_add(float* p, const float* f) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(p + i, f[i]);
+    }
+    __device__ __forceinline__ static void load(const float* p, float* f) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    }
+    __device__ __forceinline__ static void store(float* p, const float* f) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+};
+
+__device__ __forceinline__ void red_add2(float* p, float a, float b) { atomicAdd(p, a); atomicAdd(p + 1, b); }
+__device__ __forceinline__ void red_add2(__nv_bfloat16* p, float a, float b) {
+    atomicAdd(reinterpret_cast<__nv_bfloat162*>(p), __floats2bfloat162_rn(a, b));
+}
+
+// dX[row] += sum over the channels c' whose arg-max is `row` of sp[b, c'] W[c', :].
+// The arg-max rows of a cloud are very unevenly used (a few "critical" points win hundreds of channels), so the work is
+// balanced by ENTRY, not by row: one block per cloud sorts its C (row, channel) pairs (bitonic, shared memory), every warp
+// then walks 32 consecutive sorted entries, lanes across the row in 16-byte chunks (KV chunks per lane). A run of equal
+// rows inside a warp is written by that warp alone; the runs touching a warp's first / last entry go to shared memory and
+// are merged in warp order by a last pass. Every element of dX receives exactly ONE add (issued as a fire-and-forget RED
+// so that no warp waits for a row) of a sum formed in a fixed order: deterministic.
+template <typename T, int KV>
+__global__ void __launch_bounds__(1024)
+pool_lin_sparse_dx_kernel(const float* __restrict__ sp, const int32_t* __restrict__ arg, const T* __restrict__ w, int ldw,
+                          int N, int C, int log2C, int K, T* __restrict__ dx, int ld_dx) {
+    constexpr int V = Chunk<T>::N;
+    extern __shared__ unsigned char pl_smem[];
+    const int nw = C >> 5;
+    unsigned* key_s = reinterpret_cast<unsigned*>(pl_smem);                    // [C]
+    float* s_s = reinterpret_cast<float*>(key_s + C);                          // [C]
+    int* rows_s = reinterpret_cast<int*>(s_s + C);                             // [nw][2]
+    float* part_s = reinterpret_cast<float*>(rows_s + 2 * nw);                 // [nw][2][K]
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int lane = t & 31, wi = t >> 5;
+    {
+        const int row = __ldg(arg + (long long)b * C + t);
+        key_s[t] = (row >= 0 && row < N) ? ((unsigned)row << log2C) | (unsigned)t : 0xffffffffu;
+        s_s[t] = __ldg(sp + (long long)b * C + t);
+    }
+    __syncthreads();
+    for (int k = 2; k <= C; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int p = t ^ j;
+            if (p > t) {
+                const unsigned x0 = key_s[t], x1 = key_s[p];
+                const bool up = (t & k) == 0;
+                if ((x0 > x1) == up) { key_s[t] = x1; key_s[p] = x0; }
+            }
+            __syncthreads();
+        }
+    }
+    const int chunks = K / V;                              // 16-byte chunks per row; lane owns chunks lane, lane + 32, ...
+    T* dxb = dx + (long long)b * N * ld_dx;
+    float acc[KV][V];
+#pragma unroll
+    for (int q = 0; q < KV; ++q)
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
+    int cur = -1;
+    bool first = true;
+    int head_row = -1, tail_row = -1;
+    auto emit = [&](bool last) {
+        // the run `cur` is complete (or the warp's entries are): first run -> head slot, last -> tail slot, else global
+        if (cur < 0) return;
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+            const int ch = lane + 32 * q;
+            if (ch < chunks) {
+                if (first || last) {
+                    float* ps = part_s + ((long long)wi * 2 + (first ? 0 : 1)) * K + ch * V;
+#pragma unroll
+                    for (int i = 0; i < V; ++i) ps[i] = acc[q][i];
+                } else {
+                    // one add per element of this row in the whole kernel (single writer): order-independent, and the
+                    // warp does not wait for the row to come back
+                    Chunk<T>::red_add(dxb + (long long)cur * ld_dx + ch * V, acc[q]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
+        }
+        if (first) head_row = cur; else if (last) tail_row = cur;
+        first = false;
+    };
+    const unsigned cmask = (unsigned)C - 1u;
+    for (int i0 = 0; i0 < 32; i0 += 8) {
+        // eight entries per round: their W chunks are all requested before the first one is used
+        unsigned keys[8];
+        float scs[8];
+        uint4 raw[8][KV];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            keys[u] = key_s[wi * 32 + i0 + u];                               // broadcast read
+            const int c2 = keys[u] == 0xffffffffu ? 0 : (int)(keys[u] & cmask);
+            scs[u] = s_s[c2];
+            const T* wr = w + (long long)c2 * ldw;
+#pragma unroll
+            for (int q = 0; q < KV; ++q) {
+                const int ch = lane + 32 * q;
+                raw[u][q] = ch < chunks ? __ldg(reinterpret_cast<const uint4*>(wr + ch * V)) : make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (keys[u] != 0xffffffffu) {                                    // invalid entries sort last (warp-uniform)
+                const int row = (int)(keys[u] >> log2C);
+                if (row != cur) { emit(false); cur = row; }
+#pragma unroll
+                for (int q = 0; q < KV; ++q) {
+                    float f[V];
+                    Chunk<T>::decode(raw[u][q], f);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[q][j] = fmaf(scs[u], f[j], acc[q][j]);
+                }
+            }
+        }
+    }
+    emit(true);
+    if (lane == 0) { rows_s[2 * wi] = head_row; rows_s[2 * wi + 1] = tail_row; }
+    __syncthreads();
+    // merge the boundary runs in warp order: thread = column pair (one add per element, as above)
+    for (int col = 2 * t; col < K; col += 2 * blockDim.x) {
+        int r0 = -1;
+        float v0 = 0.f, v1 = 0.f;
+        for (int q = 0; q < 2 * nw; ++q) {
+            const int r = rows_s[q];
+            if (r < 0) continue;
+            if (r != r0) {
+                if (r0 >= 0) red_add2(dxb + (long long)r0 * ld_dx + col, v0, v1);
+                r0 = r;
+                v0 = v1 = 0.f;
+            }
+            v0 += part_s[(long long)q * K + col];
+            v1 += part_s[(long long)q * K + col + 1];
+        }
+        if (r0 >= 0) red_add2(dxb + (long long)r0 * ld_dx + col, v0, v1);
+    }
+}
+
+// dW[c, :] = sum_b sp[b, c] X[b N + arg[b, c], :] + a_c colsum(X) + b_c (W G)[c, :]. One warp per output channel, lanes
+// across the row in 16-byte chunks; (row, scale) of 32 clouds are fetched by the lanes at once and broadcast.
+template <typename T, int KV>
+__global__ void __launch_bounds__(256)
+pool_lin_dw_kernel(const float* __restrict__ sp, const int32_t* __restrict__ arg, const T* __restrict__ x, int ldx, int B,
+                   int N, int C, int K, const float* __restrict__ a, const float* __restrict__ bvec,
+                   const float* __restrict__ colsum, const float* __restrict__ wg, float* __restrict__ dw) {
+    constexpr int V = Chunk<T>::N;
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int chunks = K / V;
+    float acc[KV][V];
+#pragma unroll
+    for (int q = 0; q < KV; ++q)
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+        const int mb = b0 + lane;
+        int row_l = mb < B ? __ldg(arg + (long long)mb * C + c) : -1;
+        if (row_l >= N) row_l = -1;
+        const float s_l = row_l >= 0 ? __ldg(sp + (long long)mb * C + c) : 0.f;
+        const int nb = B - b0 < 32 ? B - b0 : 32;
+        for (int u0 = 0; u0 < nb; u0 += 8) {
+            float scs[8];
+            uint4 raw[8][KV];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int row = __shfl_sync(FS_FULL_MASK, row_l, (u0 + u) & 31);
+                const float sc = __shfl_sync(FS_FULL_MASK, s_l, (u0 + u) & 31);
+                const bool ok = u0 + u < nb && row >= 0;
+                scs[u] = ok ? sc : 0.f;
+                const T* xr = x + ((long long)(ok ? b0 + u0 + u : 0) * N + (ok ? row : 0)) * ldx;
+#pragma unroll
+                for (int q = 0; q < KV; ++q) {
+                    const int ch = lane + 32 * q;
+                    raw[u][q] = ch < chunks ? __ldg(reinterpret_cast<const uint4*>(xr + ch * V)) : make_uint4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int q = 0; q < KV; ++q) {
+                    float f[V];
+                    Chunk<T>::decode(raw[u][q], f);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[q][j] = fmaf(scs[u], f[j], acc[q][j]);
+                }
+            }
+        }
+    }
+    const float ac = a ? __ldg(a + c) : 0.f, bc = bvec ? __ldg(bvec + c) : 0.f;
+#pragma unroll
+    for (int q = 0; q < KV; ++q) {
+        const int ch = lane + 32 * q;
+        if (ch < chunks) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const int col = ch * V + j;
+                float v = acc[q][j];
+                if (colsum) v = fmaf(ac, __ldg(colsum + col), v);
+                if (wg) v = fmaf(bc, __ldg(wg + (long long)c * K + col), v);
+                dw[(long long)c * K + col] = v;
+            }
+        }
+    }
+}
+
+// Column sums of a (rows, K) table: per-block partials (fixed chunking) and a second pass over the partials, so the
+// result is deterministic. blockDim 256; V values per thread, K / V threads per row.
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const T* __restrict__ x, int ld, long long rows, int K, float* __restrict__ partial) {
+    extern __shared__ float cs_s[];            // [rows_per_pass][K]
+    const int tpr = K / V;
+    const int rpp = 256 / tpr;
+    const int r = threadIdx.x / tpr, v0 = (threadIdx.x - r * tpr) * V;
+    const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
+    const long long r_begin = (long long)blockIdx.x * chunk;
+    const long long r_end = r_begin + chunk < rows ? r_begin + chunk : rows;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    if (r < rpp) {
+        for (long long rr = r_begin + r; rr < r_end; rr += 8 * rpp) {
+            float f[8][V];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const long long q = rr + (long long)u * rpp;
+                const T* p = x + (q < r_end ? q : rr) * ld + v0;
+                if (V == 8) {
+                    const uint4 pk = __ldg(reinterpret_cast<const uint4*>(p));
+                    fs_bf16x8_to_float(pk, f[u]);
+                } else {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+                    f[u][0] = t.x; f[u][1] = t.y; f[u][2] = t.z; f[u][3] = t.w;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (rr + (long long)u * rpp < r_end) {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) acc[i] += f[u][i];
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) cs_s[r * K + v0 + i] = acc[i];
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < K; col += blockDim.x) {
+        float t = 0.f;
+        for (int q = 0; q < rpp; ++q) t += cs_s[q * K + col];
+        partial[(long long)blockIdx.x * K + col] = t;
+    }
+}
+// block = 32 columns x 8 partial groups; fixed order within a group, fixed order over the groups
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int G, int K, float* __restrict__ out) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    float t = 0.f;
+    if (col < K) {
+#pragma unroll 8
+        for (int g = grp; g < G; g += 8) t += __ldg(partial + (long long)g * K + col);
+    }
+    red[grp][lane] = t;
+    __syncthreads();
+    if (grp == 0 && col < K) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += red[q][lane];
+        out[col] = v;
+    }
+}
+
+// ---- feature table: [x1 | x2 | ...] (fp32, point-major) -> one (P, sum C_i) table in the compute dtype, and back
+struct CatSrc {
+    const float* p[4];
+    float* q[4];
+    int ld[4];
+    int c0[5];        // prefix sums of the widths; c0[n] = total
+    int n;
+};
+
+template <typename OT, int V>
+__global__ void __launch_bounds__(256)
+cat_cast_kernel(CatSrc s, unsigned rows, OT* __restrict__ out, int ld_out) {
+    const unsigned groups = (unsigned)s.c0[s.n] / V;
+    const unsigned total = rows * groups;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const unsigned r = e / groups;
+        const int col = (int)(e - r * groups) * V;
+        int i = 0;
+#pragma unroll
+        for (int t = 1; t < 4; ++t) i += (t < s.n && col >= s.c0[t]) ? 1 : 0;
+        const float* sp = s.p[i] + (long long)r * s.ld[i] + (col - s.c0[i]);
+        float f[V];
+#pragma unroll
+        for (int q = 0; q < V / 4; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(sp) + q);
+            f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+        }
+        OT* o = out + (long long)r * ld_out + col;
+        if (sizeof(OT) == 2) {
+            __nv_bfloat162 h[V / 2];
+#pragma unroll
+            for (int q = 0; q < V / 2; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+            if (V == 8) *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
+            else *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(h);
+        } else {
+#pragma unroll
+            for (int q = 0; q < V / 4; ++q)
+                reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        }
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+split_cast_kernel(CatSrc s, unsigned rows, const T* __restrict__ g, int ld_g) {
+    const unsigned groups = (unsigned)s.c0[s.n] / V;
+    const unsigned total = rows * groups;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const unsigned r = e / groups;
+        const int col = (int)(e - r * groups) * V;
+        int i = 0;
+#pragma unroll
+        for (int t = 1; t < 4; ++t) i += (t < s.n && col >= s.c0[t]) ? 1 : 0;
+        const T* gp = g + (long long)r * ld_g + col;
+        float f[V];
+        if (sizeof(T) == 2) {
+            if (V == 8) {
+                const uint4 pk = __ldg(reinterpret_cast<const uint4*>(gp));
+                fs_bf16x8_to_float(pk, f);
+            } else {
+                const uint2 pk = __ldg(reinterpret_cast<const uint2*>(gp));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+                const float2 lo = __bfloat1622float2(h[0]), hi = __bfloat1622float2(h[1]);
+                f[0] = lo.x; f[1] = lo.y; f[2] = hi.x; f[3] = hi.y;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < V / 4; ++q) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(gp) + q);
+                f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+            }
+        }
+        float* o = s.q[i] + (long long)r * s.ld[i] + (col - s.c0[i]);
+#pragma unroll
+        for (int q = 0; q < V / 4; ++q)
+            reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+    }
+}
+
+bool fill_cat(CatSrc& s, int n, const void* const* ptrs, const int* widths, const int* lds, bool writable) {
+    if (n < 1 || n > 4 || !ptrs || !widths || !lds) return false;
+    s.n = n;
+    s.c0[0] = 0;
+    for (int i = 0; i < 4; ++i) { s.p[i] = nullptr; s.q[i] = nullptr; s.ld[i] = 0; }
+    for (int i = 0; i < n; ++i) {
+        if (!ptrs[i] || widths[i] <= 0 || widths[i] % 4 || lds[i] < widths[i] || lds[i] % 4) return false;
+        if (writable) s.q[i] = (float*)ptrs[i]; else s.p[i] = (const float*)ptrs[i];
+        s.ld[i] = lds[i];
+        s.c0[i + 1] = s.c0[i] + widths[i];
+    }
+    for (int i = n + 1; i < 5; ++i) s.c0[i] = s.c0[n];
+    return true;
+}
+
+}  // namespace
+
+extern "C" int fs_colsum_partials(void);
+
+extern "C" int fs_pool_lin_bwd_prep(int device, fs_stream_t stream_, const float* g, const float* sel, const float* coef,
+                                    float slope, const double* dgb, double count, int train_stats, int B, int C, float* a,
+                                    float* bvec, float* sp) {
+    if (!g || !sel || !coef || !a || !bvec || !sp || B <= 0 || C <= 0) return FS_ERR_BAD_ARG;
+    if (train_stats && (!dgb || count <= 0)) return FS_ERR_BAD_ARG;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long total = (long long)B * C;
+    pool_lin_prep_kernel<<<fs_div_up(total, 256), 256, 0, stream>>>(g, sel, coef, slope, dgb, count, train_stats, B, C, a, bvec, sp);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+namespace {
+// KV = 16-byte chunks per lane: K * sizeof(T) / 16 chunks over 32 lanes
+template <typename T>
+int launch_sparse_dx(cudaStream_t stream, const float* sp, const int32_t* arg, const T* w, int ldw, int B, int N, int C, int K,
+                     T* dx, int ld_dx) {
+    int log2C = 0;
+    while ((1 << log2C) < C) ++log2C;
+    const int nw = C / 32;
+    const size_t smem = (size_t)C * 8 + (size_t)nw * 2 * 4 + (size_t)nw * 2 * K * 4;
+    const int kv = (K / Chunk<T>::N + 31) / 32;
+#define GO(KV)                                                                                                              \
+    do {                                                                                                                    \
+        FS_CUDA_TRY(cudaFuncSetAttribute(pool_lin_sparse_dx_kernel<T, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        pool_lin_sparse_dx_kernel<T, KV><<<B, C, smem, stream>>>(sp, arg, w, ldw, N, C, log2C, K, dx, ld_dx);                \
+    } while (0)
+    if (kv == 1) GO(1); else if (kv == 2) GO(2); else if (kv <= 4) GO(4); else return FS_ERR_UNSUPPORTED;
+#undef GO
+    return FS_OK;
+}
+template <typename T>
+int launch_dw(cudaStream_t stream, const float* sp, const int32_t* arg, const T* x, int ldx, int B, int N, int C, int K,
+              const float* a, const float* bvec, const float* colsum, const float* wg, float* dw) {
+    const int kv = (K / Chunk<T>::N + 31) / 32;
+    const int grid = (C + 7) / 8;
+    if (kv == 1) pool_lin_dw_kernel<T, 1><<<grid, 256, 0, stream>>>(sp, arg, x, ldx, B, N, C, K, a, bvec, colsum, wg, dw);
+    else if (kv == 2) pool_lin_dw_kernel<T, 2><<<grid, 256, 0, stream>>>(sp, arg, x, ldx, B, N, C, K, a, bvec, colsum, wg, dw);
+    else if (kv <= 4) pool_lin_dw_kernel<T, 4><<<grid, 256, 0, stream>>>(sp, arg, x, ldx, B, N, C, K, a, bvec, colsum, wg, dw);
+    else return FS_ERR_UNSUPPORTED;
+    return FS_OK;
+}
+}  // namespace
+
+extern "C" int fs_pool_lin_bwd_dx_sparse(int device, fs_stream_t stream_, const float* sp, const int32_t* arg, const void* w,
+                                         int dtype, int ldw, int B, int N, int C, int K, void* dx, int ld_dx) {
+    if (!sp || !arg || !w || !dx || B <= 0 || N <= 0 || C <= 0 || ldw < K || ld_dx < K) return FS_ERR_BAD_ARG;
+    const int V = dtype == FS_BF16 ? 8 : 4;
+    if (K % V || K > 512 || ldw % V || ld_dx % V || C < 32 || C > 1024 || (C & (C - 1)) || (long long)N * C >= (1ll << 32) - 1 ||
+        ((uintptr_t)w & 15) || ((uintptr_t)dx & 15))
+        return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int rc = dtype == FS_BF16
+        ? launch_sparse_dx(stream, sp, arg, (const __nv_bfloat16*)w, ldw, B, N, C, K, (__nv_bfloat16*)dx, ld_dx)
+        : launch_sparse_dx(stream, sp, arg, (const float*)w, ldw, B, N, C, K, (float*)dx, ld_dx);
+    if (rc != FS_OK) return rc;
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_pool_lin_bwd_dw(int device, fs_stream_t stream_, const float* sp, const int32_t* arg, const void* x, int dtype,
+                                  int ldx, int B, int N, int C, int K, const float* a, const float* bvec, const float* colsum,
+                                  const float* wg, float* dw) {
+    if (!sp || !arg || !x || !dw || B <= 0 || N <= 0 || C <= 0 || ldx < K) return FS_ERR_BAD_ARG;
+    const int V = dtype == FS_BF16 ? 8 : 4;
+    if (K % V || K > 512 || ldx % V || ((uintptr_t)x & 15)) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int rc = dtype == FS_BF16
+        ? launch_dw(stream, sp, arg, (const __nv_bfloat16*)x, ldx, B, N, C, K, a, bvec, colsum, wg, dw)
+        : launch_dw(stream, sp, arg, (const float*)x, ldx, B, N, C, K, a, bvec, colsum, wg, dw);
+    if (rc != FS_OK) return rc;
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+namespace {
+bool cat_wide(const CatSrc& s, int ld_other) {        // eight columns per thread when every width and stride allows it
+    bool ok = ld_other % 8 == 0;
+    for (int i = 0; i < s.n; ++i) ok = ok && (s.c0[i + 1] - s.c0[i]) % 8 == 0 && s.ld[i] % 8 == 0;
+    return ok;
+}
+bool cat_aligned(const void* const* ptrs, int n, const void* other) {
+    bool ok = ((uintptr_t)other & 15) == 0;
+    for (int i = 0; i < n; ++i) ok = ok && ((uintptr_t)ptrs[i] & 15) == 0;
+    return ok;
+}
+}  // namespace
+
+extern "C" int fs_colsum(int device, fs_stream_t stream_, const void* x, int dtype, int ld, long long rows, int K,
+                         float* partial_ws, float* out) {
+    const int V = dtype == FS_BF16 ? 8 : 4;
+    if (!x || !partial_ws || !out || rows <= 0 || K <= 0 || ld < K) return FS_ERR_BAD_ARG;
+    if (K % V || K / V > 256 || ld % V || ((uintptr_t)x & 15)) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int G = fs_colsum_partials();
+    const int rpp = 256 / (K / V);
+    const size_t smem = (size_t)rpp * K * sizeof(float);
+    if (dtype == FS_BF16) colsum_partial_kernel<__nv_bfloat16, 8><<<G, 256, smem, stream>>>((const __nv_bfloat16*)x, ld, rows, K, partial_ws);
+    else colsum_partial_kernel<float, 4><<<G, 256, smem, stream>>>((const float*)x, ld, rows, K, partial_ws);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    colsum_final_kernel<<<(K + 31) / 32, 256, 0, stream>>>(partial_ws, G, K, out);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_colsum_partials(void) { return 4 * FS_NUM_SMS; }
+
+extern "C" int fs_cat_cast(int device, fs_stream_t stream_, int n, const void* const* srcs, const int* widths, const int* lds,
+                           long long rows, void* out, int out_dtype, int ld_out) {
+    CatSrc s;
+    if (!out || rows <= 0 || !fill_cat(s, n, srcs, widths, lds, false) || ld_out < s.c0[n] || ld_out % 4) return FS_ERR_BAD_ARG;
+    if (!cat_aligned(srcs, n, out) || rows * (long long)(s.c0[n] / 4) >= (1ll << 31)) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool wide = cat_wide(s, ld_out);
+    const long long total = rows * (s.c0[n] / (wide ? 8 : 4));
+    const int grid = (int)(fs_div_up(total, 256) < (long long)FS_NUM_SMS * 16 ? fs_div_up(total, 256) : (long long)FS_NUM_SMS * 16);
+    if (out_dtype == FS_BF16) {
+        if (wide) cat_cast_kernel<__nv_bfloat16, 8><<<grid, 256, 0, stream>>>(s, (unsigned)rows, (__nv_bfloat16*)out, ld_out);
+        else cat_cast_kernel<__nv_bfloat16, 4><<<grid, 256, 0, stream>>>(s, (unsigned)rows, (__nv_bfloat16*)out, ld_out);
+    } else {
+        if (wide) cat_cast_kernel<float, 8><<<grid, 256, 0, stream>>>(s, (unsigned)rows, (float*)out, ld_out);
+        else cat_cast_kernel<float, 4><<<grid, 256, 0, stream>>>(s, (unsigned)rows, (float*)out, ld_out);
+    }
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_split_cast(int device, fs_stream_t stream_, int n, void* const* dsts, const int* widths, const int* lds,
+                             long long rows, const void* g, int g_dtype, int ld_g) {
+    CatSrc s;
+    if (!g || rows <= 0 || !fill_cat(s, n, (const void* const*)dsts, widths, lds, true) || ld_g < s.c0[n] || ld_g % 4) return FS_ERR_BAD_ARG;
+    if (!cat_aligned((const void* const*)dsts, n, g) || rows * (long long)(s.c0[n] / 4) >= (1ll << 31)) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool wide = cat_wide(s, ld_g);
+    const long long total = rows * (s.c0[n] / (wide ? 8 : 4));
+    const int grid = (int)(fs_div_up(total, 256) < (long long)FS_NUM_SMS * 16 ? fs_div_up(total, 256) : (long long)FS_NUM_SMS * 16);
+    if (g_dtype == FS_BF16) {
+        if (wide) split_cast_kernel<__nv_bfloat16, 8><<<grid, 256, 0, stream>>>(s, (unsigned)rows, (const __nv_bfloat16*)g, ld_g);
+        else split_cast_kernel<__nv_bfloat16, 4><<<grid, 256, 0, stream>>>(s, (unsigned)rows, (const __nv_bfloat16*)g, ld_g);
+    } else {
+        if (wide) split_cast_kernel<float, 8><<<grid, 256, 0, stream>>>(s, (unsigned)rows, (const float*)g, ld_g);
+        else split_cast_kernel<float, 4><<<grid, 256, 0, stream>>>(s, (unsigned)rows, (const float*)g, ld_g);
+    }
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}

@@ -106,11 +106,16 @@ class ConvBlock(nn.Module):
     def forward_pool_pm(self, x, B, N):
         """Conv + BatchNorm + LeakyReLU followed by the max over the N points of each cloud -> (B, C_out).
         LeakyReLU(BN(.)) is monotone per channel, so only per-cloud max/min of the GEMM output is needed."""
-        y = x @ self.weight_matrix().to(x.dtype).t()
         bn = self.norm
-        C = y.shape[1]
-        if bn is not None and self.conv.bias is None and y.is_cuda and C >= 64 and (C & (C - 1)) == 0:
-            return ops.pool_bn_act(y, bn, self.negative_slope if self.has_activation else 1.0, B, N)
+        C = self.conv.out_channels
+        fused = bn is not None and self.conv.bias is None and x.is_cuda and C >= 64 and (C & (C - 1)) == 0
+        slope = self.negative_slope if self.has_activation else 1.0
+        if fused and ops.pool_linear_supported(x, self.weight_matrix()):
+            # GEMM + pooled BatchNorm as ONE autograd node: the backward needs neither y nor the dense gradient
+            return ops.pool_linear_bn_act(x, self.weight_matrix(), bn, slope, B, N)
+        y = x @ self.weight_matrix().to(x.dtype).t()
+        if fused:
+            return ops.pool_bn_act(y, bn, slope, B, N)
         if self.conv.bias is not None:
             y = y + self.conv.bias.to(y.dtype)
         return self.norm_act_pm(y).view(B, N, -1).amax(dim=1)
@@ -191,10 +196,11 @@ class EdgeConv(nn.Module):
             return self._finish_multilayer(h, graph)
         w = first.weight_matrix()
         w_cat = ops.edge_weight_table(w, C)                                    # [W1 ; W2 - W1]  (2Cp, C)
-        # The per-point table stays fp32 in every precision mode: y = a_j + b_i = W1 (x_j - x_i) + W2 x_i
+        # The per-point table is STORED in fp32 in every precision mode: y = a_j + b_i = W1 (x_j - x_i) + W2 x_i
         # cancels the common part of a_j and -b_i, so rounding a to 16 bits would wipe out the local
-        # differences the layer is about (measured: cosine 0.998 on gradients with bf16 tables).
-        table = ops.table_gemm(x_pm.float().contiguous(), w_cat.float())
+        # differences the layer is about (measured: cosine 0.998 on gradients with bf16 tables). In the 'bf16' mode the
+        # GEMM that forms it may round its OPERANDS to TF32 (fp32 accumulation and output); 'fp32' mode does not.
+        table = ops.table_gemm(x_pm.float().contiguous(), w_cat.float(), tf32=cdt == torch.bfloat16)
         bn = first.norm
         if len(self.shared_mlp) == 1:
             return ops.edgeconv_fused(table, bn.weight, bn.bias, graph, bn.running_mean, bn.running_var,
@@ -368,7 +374,7 @@ class DGCNNSeg(DGCNNBase):
             x1 = self.ec1.forward_pm(x_pm, B, N, g, cdt)
             x2 = self.ec2.forward_pm(x1, B, N, g, cdt)
             x3 = self.ec3.forward_pm(x2, B, N, g, cdt)
-            feats = torch.cat([x1, x2, x3], dim=1).to(cdt)                       # (B*N, 192)
+            feats = ops.cat_cast([x1, x2, x3], cdt)                              # (B*N, 192), one pass
 
             glob = self.global_feature[0].forward_pool_pm(feats, B, N)           # (B, 1024), activation never written
 
@@ -414,7 +420,7 @@ class DGCNNReg(DGCNNBase):
             x2 = self.ec2.forward_pm(x1, B, N, g, cdt)
             x3 = self.ec3.forward_pm(x2, B, N, g, cdt)
             x4 = self.ec4.forward_pm(x3, B, N, g, cdt)
-            feats = torch.cat([x1, x2, x3, x4], dim=1).to(cdt)
+            feats = ops.cat_cast([x1, x2, x3, x4], cdt)
             glob = self.global_feature[0].forward_pool_pm(feats, B, N)                   # (B, 1024)
             h = glob
             for layer in self.regression:

@@ -4,6 +4,7 @@ reduction for Chamfer. Tensors are torch CUDA tensors; the arithmetic runs in li
 Layout convention: "point-major" tables of shape (P, C) with P = B*N rows (row = b*N + n) and unit
 stride along C. The reference's (B, C, N) tensors are converted at the module boundary only.
 """
+import ctypes
 import os
 
 import torch
@@ -563,38 +564,195 @@ def pool_bn_act(x, bn, slope, B, N):
                               bn.training, bn.eps, bn.momentum, slope, B, N)
 
 
+USE_POOL_GRAM = os.environ.get("FS_POOL_GRAM", "1") != "0"
+
+
+def _gram_f32(x):
+    """X^T X with fp32 accumulation AND fp32 output (a bf16 output would lose the covariance to rounding)."""
+    if x.dtype == torch.float32:
+        return x.t() @ x
+    return torch.mm(x.t(), x, out_dtype=torch.float32)
+
+
+class _PoolLinearFn(torch.autograd.Function):
+    """out (B, C) = max over the N rows of each cloud of LeakyReLU(BatchNorm(X W^T)): Conv1d + BN + LeakyReLU +
+    AdaptiveMaxPool1d of the global feature (models/dgcnn.py:123-126, 156). Forward: library GEMM, then one pass that
+    keeps only per-cloud max/min + statistics (the activation is never written and the GEMM output is NOT kept for
+    backward). Backward: dy = S + a + b*y with one non-zero of S per (cloud, channel), so with y = X W^T
+        dX = S W + 1 (a^T W) + X (W^T diag(b) W),      dW = S^T X + a colsum(X)^T + diag(b) W (X^T X)
+    - K x K products instead of the P x C gradient (csrc/heads.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, running_mean, running_var, nbt, training, eps, momentum, slope, B, N):
+        wc = w.detach().to(x.dtype).contiguous()              # (C, K)
+        C = wc.shape[0]
+        dev = x.device
+        y = x @ wc.t()
+        gamma32, beta32 = gamma.detach().float(), beta.detach().float()
+        sel = torch.empty(B, C, dtype=torch.float32, device=dev)
+        arg = torch.empty(B, C, dtype=torch.int32, device=dev)
+        stats = _stats_buffer(C, dev) if training else None
+        packed = _zeros64(B * C, dev).view(torch.int64)
+        _lib.call("fs_pool_reduce", y, y, _lib.dtype_code(y), y.stride(0), B, N, C, gamma32, sel, arg, stats, packed)
+        coef = _bn_coef(y, stats, B * N, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
+        out = torch.empty(B, C, dtype=x.dtype, device=dev)
+        _lib.call("fs_bn_act_apply", y, sel, 0, C, B, C, None, 1, coef, float(slope), out, _lib.dtype_code(out), C)
+        ctx.save_for_backward(x, wc, sel, arg, coef)
+        ctx.training, ctx.slope, ctx.B, ctx.N, ctx.w_dtype = training, slope, B, N, w.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wc, sel, arg, coef = ctx.saved_tensors
+        B, N, C, K = ctx.B, ctx.N, wc.shape[0], wc.shape[1]
+        dev = x.device
+        g32 = g.float().contiguous()
+        dgb = _stats_buffer(C, dev)
+        _lib.call("fs_bn_act_bwd", x, g32, 0, C, sel, 0, C, B, C, None, 1, coef, float(ctx.slope), dgb, float(B * N),
+                  int(ctx.training), None, 0, C)
+        vec = torch.empty(2 * C + B * C, dtype=torch.float32, device=dev)
+        a, bvec, sp = vec[:C], vec[C:2 * C], vec[2 * C:]
+        _lib.call("fs_pool_lin_bwd_prep", x, g32, sel, coef, float(ctx.slope), dgb, float(B * N), int(ctx.training), B, C,
+                  a, bvec, sp)
+        w32 = wc.float()
+        dx = dw = None
+        colsum = wg = None
+        if ctx.training:
+            with _matmul_tf32(False):     # the K x K factors carry a covariance (cancellation): full fp32 products
+                if ctx.needs_input_grad[0]:
+                    m = (w32 * bvec.unsqueeze(1)).t() @ w32                              # W^T diag(b) W   (K, K)
+                    r = a @ w32                                                          # a^T W           (K,)
+                    dx = torch.addmm(r.to(x.dtype), x, m.to(x.dtype))
+                if ctx.needs_input_grad[1]:
+                    colsum = torch.empty(K, dtype=torch.float32, device=dev)
+                    partial = _workspace(4 * K * _lib.load().fs_colsum_partials(), dev, "colsum")
+                    _lib.call("fs_colsum", x, x, _lib.dtype_code(x), x.stride(0), B * N, K, partial, colsum)
+                    wg = (w32 @ _gram_f32(x)).contiguous()                               # W (X^T X)       (C, K)
+        elif ctx.needs_input_grad[0]:
+            dx = torch.zeros_like(x)
+        if dx is not None:
+            _lib.call("fs_pool_lin_bwd_dx_sparse", x, sp, arg, wc, _lib.dtype_code(wc), wc.stride(0), B, N, C, K, dx,
+                      dx.stride(0))
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(C, K, dtype=torch.float32, device=dev)
+            _lib.call("fs_pool_lin_bwd_dw", x, sp, arg, x, _lib.dtype_code(x), x.stride(0), B, N, C, K,
+                      a if ctx.training else None, bvec if ctx.training else None, colsum, wg, dw)
+            dw = dw.to(ctx.w_dtype)
+        dgb32 = dgb[:2 * C].float()
+        return dx, dw, dgb32[C:], dgb32[:C], None, None, None, None, None, None, None, None, None
+
+
+def pool_linear_supported(x, w):
+    K = x.shape[1]
+    return (USE_POOL_GRAM and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous()
+            and K % 32 == 0 and K <= 512 and w.shape[1] == K and 64 <= w.shape[0] <= 1024
+            and (w.shape[0] & (w.shape[0] - 1)) == 0)
+
+
+def pool_linear_bn_act(x, w, bn, slope, B, N):
+    """x (B*N, K) contiguous, w (C, K): Conv1d(k=1, bias=False) + BN + LeakyReLU + max over the points of each cloud."""
+    return _PoolLinearFn.apply(x, w, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                               bn.training, bn.eps, bn.momentum, slope, B, N)
+
+
+def _host_arrays(tensors):
+    n = len(tensors)
+    ptrs = (ctypes.c_void_p * 4)(*([t.data_ptr() for t in tensors] + [None] * (4 - n)))
+    widths = (ctypes.c_int * 4)(*([t.shape[1] for t in tensors] + [0] * (4 - n)))
+    lds = (ctypes.c_int * 4)(*([t.stride(0) for t in tensors] + [0] * (4 - n)))
+    return ptrs, widths, lds
+
+
+class _CatCastFn(torch.autograd.Function):
+    """torch.cat((x1, x2, ...), dim=1).to(dtype) of fp32 point-major tables in one pass (models/dgcnn.py:154, 200);
+    the gradient comes back as contiguous fp32 tables, one pass as well."""
+
+    @staticmethod
+    def forward(ctx, dtype, *xs):
+        rows = xs[0].shape[0]
+        total = sum(t.shape[1] for t in xs)
+        out = torch.empty(rows, total, dtype=dtype, device=xs[0].device)
+        ptrs, widths, lds = _host_arrays(xs)
+        _lib.call("fs_cat_cast", out, len(xs), ptrs, widths, lds, rows, out, _lib.dtype_code(out), out.stride(0))
+        ctx.widths = [t.shape[1] for t in xs]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        rows = g.shape[0]
+        outs = [torch.empty(rows, c, dtype=torch.float32, device=g.device) for c in ctx.widths]
+        ptrs, widths, lds = _host_arrays(outs)
+        _lib.call("fs_split_cast", g, len(outs), ptrs, widths, lds, rows, g, _lib.dtype_code(g), g.stride(0))
+        return (None, *outs)
+
+
+def cat_cast(xs, dtype):
+    """[x1 | x2 | ...] of fp32 (rows, C_i) tables as one (rows, sum C_i) table in `dtype` (fp32 or bf16)."""
+    ok = (1 <= len(xs) <= 4 and all(t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1
+                                    and t.shape[1] % 4 == 0 and t.stride(0) % 4 == 0 for t in xs)
+          and dtype in (torch.float32, torch.bfloat16))
+    if not ok:
+        return torch.cat(list(xs), dim=1).to(dtype)
+    return _CatCastFn.apply(dtype, *xs)
+
+
 # ------------------------------------------------------------------------------------------- per-point GEMM
+
+class _matmul_tf32:
+    """Scoped torch.backends.cuda.matmul.allow_tf32: the product decides per call whether an fp32 GEMM may round its
+    operands to TF32, instead of inheriting whatever the process set globally."""
+
+    def __init__(self, allow):
+        self.allow = bool(allow)
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.allow
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
 
 class _TableGemmFn(torch.autograd.Function):
     """T = X W^T for a tall-skinny X (P x C, P ~ 1e5) and a small W (2Cp x C). The weight gradient
     dW = dT^T X has a P-long reduction dimension and a tiny output; as one GEMM it runs on a few dozen CTAs,
-    so it is issued as a batched GEMM over row chunks followed by a sum over the chunks."""
+    so it is issued as a batched GEMM over row chunks followed by a sum over the chunks.
+    tf32: operands rounded to TF32 (10-bit mantissa) on the tensor cores, fp32 accumulation and output - the 'bf16'
+    precision mode; the 'fp32' mode keeps full fp32 products."""
 
     @staticmethod
-    def forward(ctx, x, w):
+    def forward(ctx, x, w, tf32):
         ctx.save_for_backward(x, w)
-        return x @ w.t()
+        ctx.tf32 = tf32
+        with _matmul_tf32(tf32):
+            return x @ w.t()
 
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
         gx = gw = None
-        if ctx.needs_input_grad[0]:
-            gx = g @ w
-        if ctx.needs_input_grad[1]:
-            P = x.shape[0]
-            S = 1
-            while S < 128 and P % (2 * S) == 0 and P // (2 * S) >= 256:
-                S *= 2
-            if S > 1 and g.is_contiguous() and x.is_contiguous():
-                gw = torch.bmm(g.view(S, P // S, -1).transpose(1, 2), x.view(S, P // S, -1)).sum(dim=0)
-            else:
-                gw = g.t() @ x
-        return gx, gw
+        with _matmul_tf32(ctx.tf32):
+            if ctx.needs_input_grad[0]:
+                gx = g @ w
+            if ctx.needs_input_grad[1]:
+                P = x.shape[0]
+                S = 1
+                while S < 128 and P % (2 * S) == 0 and P // (2 * S) >= 256:
+                    S *= 2
+                if S > 1 and g.is_contiguous() and x.is_contiguous():
+                    gw = torch.bmm(g.view(S, P // S, -1).transpose(1, 2), x.view(S, P // S, -1)).sum(dim=0)
+                else:
+                    gw = g.t() @ x
+        return gx, gw, None
 
 
-def table_gemm(x, w):
-    return _TableGemmFn.apply(x, w)
+def table_gemm(x, w, tf32=False):
+    return _TableGemmFn.apply(x, w, tf32)
 
 
 class _EdgeWeightFn(torch.autograd.Function):

@@ -319,6 +319,44 @@ int fs_pool_bwd(int device, fs_stream_t stream, const void* x, int dtype, int ld
                 const float* g, const float* sel, const int32_t* arg, const float* coef, float slope,
                 const double* dgb, double count, int train_stats, void* dx, int dx_dtype, int ld_dx);
 
+/*
+ * Backward of the pooled layer  out[b,c] = max_r LeakyReLU(BN(X W^T))[r,c]  (global_feature, models/dgcnn.py:123-126,
+ * 156) WITHOUT the dense [B*N, C] gradient: dy[r,c] = S[r,c] + a_c + b_c y[r,c] with one non-zero of S per (cloud,
+ * channel), hence
+ *     dX = S W + 1 (a^T W) + X (W^T diag(b) W)          dW = S^T X + a colsum(X)^T + diag(b) W (X^T X)
+ * The K x K products are library GEMMs on the caller's side; these entry points are the rest:
+ *   fs_pool_lin_bwd_prep       a [C], bvec [C], sp [B,C] = scale * g * LeakyReLU'(z_sel) from g [B,C], sel [B,C],
+ *                              coef [4C] (fs_bn_finalize layout) and dgb [2C] (double; fs_bn_act_bwd on the B x C
+ *                              selected values)
+ *   fs_pool_lin_bwd_dx_sparse  dx[b*N + arg[b,c], :] += sp[b,c] * w[c, :]   (w [C,K], dx [B*N,K], same dtype; every
+ *                              row has one writer and a fixed summation order: deterministic, no atomics)
+ *   fs_pool_lin_bwd_dw         dw [C,K] f32 = S^T X + a colsum^T + diag(bvec) wg  (a / bvec / colsum / wg nullable:
+ *                              eval-mode statistics have no dense part); K % 32 == 0, K <= 512
+ */
+/* Column sums of x [rows, K] (fp32 or bf16; K % 8 == 0 (bf16) / % 4 (fp32), 16-byte aligned rows) -> out [K] f32, through
+ * fs_colsum_partials() x K fp32 partials in partial_ws (fixed chunking: deterministic). */
+int fs_colsum_partials(void);
+int fs_colsum(int device, fs_stream_t stream, const void* x, int dtype, int ld, long long rows, int K,
+              float* partial_ws, float* out);
+int fs_pool_lin_bwd_prep(int device, fs_stream_t stream, const float* g, const float* sel, const float* coef,
+                         float slope, const double* dgb, double count, int train_stats, int B, int C, float* a,
+                         float* bvec, float* sp);
+int fs_pool_lin_bwd_dx_sparse(int device, fs_stream_t stream, const float* sp, const int32_t* arg, const void* w,
+                              int dtype, int ldw, int B, int N, int C, int K, void* dx, int ld_dx);
+int fs_pool_lin_bwd_dw(int device, fs_stream_t stream, const float* sp, const int32_t* arg, const void* x, int dtype,
+                       int ldx, int B, int N, int C, int K, const float* a, const float* bvec, const float* colsum,
+                       const float* wg, float* dw);
+
+/*
+ * Feature table of the heads: torch.cat((x1, x2, x3), dim=1) (models/dgcnn.py:154, 200) of n <= 4 fp32 point-major
+ * tables [rows, widths[i]] (row strides lds[i], widths % 4 == 0) written once in the compute dtype, and the reverse for
+ * the gradient (g [rows, sum widths] -> n contiguous fp32 tables). srcs / dsts / widths / lds are HOST arrays of n.
+ */
+int fs_cat_cast(int device, fs_stream_t stream, int n, const void* const* srcs, const int* widths, const int* lds,
+                long long rows, void* out, int out_dtype, int ld_out);
+int fs_split_cast(int device, fs_stream_t stream, int n, void* const* dsts, const int* widths, const int* lds,
+                  long long rows, const void* g, int g_dtype, int ld_g);
+
 /* ---------------------------------------------------------------- Chamfer ------------------ */
 
 /*

@@ -78,3 +78,76 @@ def test_pool_bn_act_matches_torch(lib, B, N, C, training, dtype):
     assert rel_err(bn_gpu.bias.grad, bn_ref.bias.grad) < gtol
     if training:
         assert_close(bn_gpu.running_var, bn_ref.running_var, 1e-4, 1e-6, "running_var")
+
+
+@pytest.mark.parametrize("B,N,K,C,training,dtype", [(4, 1000, 192, 1024, True, torch.float32),
+                                                    (2, 2048, 128, 1024, False, torch.float32),
+                                                    (3, 777, 512, 256, True, torch.float32)])
+def test_pool_linear_matches_torch(lib, B, N, K, C, training, dtype):
+    """Conv1d(k=1) + BN + LeakyReLU + max over points as ONE node (ops.pool_linear_bn_act): the backward works on
+    K x K products (no P x C gradient). Reference: the same layer in plain PyTorch, fp64 so that the comparison measures
+    the kernel and not the reference's own fp32 noise. (bf16: next test - rounding y moves arg-max rows, so the fair
+    reference there is the materialised path on the same rounded y.)"""
+    gen = torch.Generator().manual_seed(B * N + C + K)
+    x = torch.relu(torch.randn(B * N, K, generator=gen) + 0.3) + 0.05 * torch.randn(B * N, K, generator=gen)
+    w = torch.randn(C, K, generator=gen) / K ** 0.5
+    gout = torch.randn(B, C, generator=gen)
+    bn_ref, bn_gpu = _bn(C, 5).double(), _bn(C, 5).to(DEV)
+    bn_ref.train(training); bn_gpu.train(training)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yr = xr @ wr.t()
+    ref = F.adaptive_max_pool1d(F.leaky_relu(bn_ref(yr), 0.2).view(B, N, C).transpose(1, 2), 1).squeeze(-1)
+    ref.backward(gout.double())
+    xg = x.to(DEV).to(dtype).requires_grad_(True)
+    wg = w.to(DEV).requires_grad_(True)
+    assert ops.pool_linear_supported(xg, wg)
+    out = ops.pool_linear_bn_act(xg, wg, bn_gpu, 0.2, B, N)
+    out.float().backward(gout.to(DEV))
+    # bf16: the GEMM output is rounded to bf16 before the statistics / arg-max (as in the materialised path)
+    tol = 2e-4 if dtype == torch.float32 else 2e-2
+    assert_close(out.float(), ref.float(), tol, tol, "pooled output")
+    gtol = 5e-4 if dtype == torch.float32 else 3e-2
+    assert rel_err(xg.grad.float(), xr.grad.float()) < gtol, rel_err(xg.grad.float(), xr.grad.float())
+    assert rel_err(wg.grad, wr.grad.float()) < gtol, rel_err(wg.grad, wr.grad.float())
+    assert rel_err(bn_gpu.weight.grad, bn_ref.weight.grad.float()) < gtol
+    assert rel_err(bn_gpu.bias.grad, bn_ref.bias.grad.float()) < gtol
+    if training:
+        assert_close(bn_gpu.running_var, bn_ref.running_var.float(), 1e-3 if dtype == torch.float32 else 1e-2, 1e-6, "running_var")
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 2e-2)])
+def test_pool_linear_equals_materialised_path(lib, dtype, tol):
+    """Same inputs through the dense-gradient kernels and the K x K formulation: gradients agree to fp32 noise (fp32) /
+    to the bf16 rounding of the dense gradient that the materialised path stores (bf16)."""
+    B, N, K, C = 4, 1024, 192, 1024
+    gen = torch.Generator().manual_seed(9)
+    x = torch.relu(torch.randn(B * N, K, generator=gen)).to(DEV).to(dtype)
+    w = (torch.randn(C, K, generator=gen) / K ** 0.5).to(DEV).to(dtype).float()
+    gout = torch.randn(B, C, generator=gen).to(DEV)
+    res = []
+    for fused in (False, True):
+        bn = _bn(C, 5).to(DEV)
+        xg, wg = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        out = ops.pool_linear_bn_act(xg, wg, bn, 0.2, B, N) if fused else ops.pool_bn_act(xg @ wg.to(dtype).t(), bn, 0.2, B, N)
+        out.float().backward(gout)
+        res.append((out.detach().float(), xg.grad.float(), wg.grad, bn.weight.grad, bn.bias.grad))
+    for a, b, name in zip(res[0], res[1], ("out", "dx", "dw", "dgamma", "dbeta")):
+        assert rel_err(b, a) < tol, (name, rel_err(b, a))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cat_cast_matches_torch(lib, dtype):
+    gen = torch.Generator().manual_seed(4)
+    rows = 5000
+    xs = [torch.randn(rows, c, generator=gen).to(DEV).requires_grad_(True) for c in (64, 64, 128, 256)]
+    wide = torch.randn(rows, 80, generator=gen).to(DEV)
+    xs[1] = wide[:, 8:72].detach().requires_grad_(True)                       # strided source (ld 80)
+    out = ops.cat_cast(xs, dtype)
+    ref = torch.cat([t.detach() for t in xs], dim=1).to(dtype)
+    assert torch.equal(out, ref)
+    g = torch.randn(rows, 512, generator=gen).to(DEV).to(dtype)
+    out.backward(g)
+    off = 0
+    for t in xs:
+        assert torch.equal(t.grad, g[:, off:off + t.shape[1]].float())
+        off += t.shape[1]

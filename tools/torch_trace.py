@@ -28,3 +28,12 @@ for t, n, sh, st in rows:
     agg[(n, sh, st)][0] += 1; agg[(n, sh, st)][1] += t
 for (n, sh, st), (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print("%7.1f us x%2d  %-28s %-60s %s" % (t, c, n, sh, st))
+print("---- kernels")
+kagg = collections.defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        kagg[e.name[:90]][0] += 1; kagg[e.name[:90]][1] += e.device_time_total
+tot = sum(v[1] for v in kagg.values())
+print("total kernel us", tot, "kernels", sum(v[0] for v in kagg.values()))
+for n, (c, t) in sorted(kagg.items(), key=lambda kv: -kv[1][1])[:int(sys.argv[1]) if len(sys.argv) > 1 else 60]:
+    print("%7.1f us x%2d  %s" % (t, c, n))
