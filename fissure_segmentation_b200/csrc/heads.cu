@@ -79,31 +79,20 @@ __device__ __forceinline__ void red_add2(__nv_bfloat16* p, float a, float b) {
     atomicAdd(reinterpret_cast<__nv_bfloat162*>(p), __floats2bfloat162_rn(a, b));
 }
 
-// dX[row] += sum over the channels c' whose arg-max is `row` of sp[b, c'] W[c', :].
+// dX[row] += sum over the channels c' whose arg-max is `row` of sp[b, c'] W[c', :], in three small kernels.
 // The arg-max rows of a cloud are very unevenly used (a few "critical" points win hundreds of channels), so the work is
-// balanced by ENTRY, not by row: one block per cloud sorts its C (row, channel) pairs (bitonic, shared memory), every warp
-// then walks 32 consecutive sorted entries, lanes across the row in 16-byte chunks (KV chunks per lane). A run of equal
-// rows inside a warp is written by that warp alone; the runs touching a warp's first / last entry go to shared memory and
-// are merged in warp order by a last pass. Every element of dX receives exactly ONE add (issued as a fire-and-forget RED
-// so that no warp waits for a row) of a sum formed in a fixed order: deterministic.
-template <typename T, int KV>
+// balanced by ENTRY, not by row: (1) one block per cloud sorts its C (row, channel) pairs (bitonic, shared memory);
+// (2) every warp of the grid walks 32 consecutive sorted entries, lanes across the row in 16-byte chunks (KV chunks per
+// lane, eight entries' W chunks in flight). A run of equal rows inside a warp is added to dX by that warp alone; the runs
+// touching a warp's first / last entry go to a partial buffer; (3) one block per cloud merges those partials in warp
+// order. Every element of dX receives exactly ONE add (issued as a fire-and-forget RED so that no warp waits for a row)
+// of a sum formed in a fixed order: deterministic. (One kernel doing all three on 32 SMs took 41 us; instruction-bound.)
 __global__ void __launch_bounds__(1024)
-pool_lin_sparse_dx_kernel(const float* __restrict__ sp, const int32_t* __restrict__ arg, const T* __restrict__ w, int ldw,
-                          int N, int C, int log2C, int K, T* __restrict__ dx, int ld_dx) {
-    constexpr int V = Chunk<T>::N;
-    extern __shared__ unsigned char pl_smem[];
-    const int nw = C >> 5;
-    unsigned* key_s = reinterpret_cast<unsigned*>(pl_smem);                    // [C]
-    float* s_s = reinterpret_cast<float*>(key_s + C);                          // [C]
-    int* rows_s = reinterpret_cast<int*>(s_s + C);                             // [nw][2]
-    float* part_s = reinterpret_cast<float*>(rows_s + 2 * nw);                 // [nw][2][K]
+pool_lin_sort_kernel(const int32_t* __restrict__ arg, int N, int C, int log2C, unsigned* __restrict__ keys) {
+    extern __shared__ unsigned key_s[];                                        // [C]
     const int b = blockIdx.x, t = threadIdx.x;
-    const int lane = t & 31, wi = t >> 5;
-    {
-        const int row = __ldg(arg + (long long)b * C + t);
-        key_s[t] = (row >= 0 && row < N) ? ((unsigned)row << log2C) | (unsigned)t : 0xffffffffu;
-        s_s[t] = __ldg(sp + (long long)b * C + t);
-    }
+    const int row = __ldg(arg + (long long)b * C + t);
+    key_s[t] = (row >= 0 && row < N) ? ((unsigned)row << log2C) | (unsigned)t : 0xffffffffu;
     __syncthreads();
     for (int k = 2; k <= C; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -116,8 +105,24 @@ pool_lin_sparse_dx_kernel(const float* __restrict__ sp, const int32_t* __restric
             __syncthreads();
         }
     }
+    keys[(long long)b * C + t] = key_s[t];
+}
+
+template <typename T, int KV>
+__global__ void __launch_bounds__(128)
+pool_lin_rows_kernel(const unsigned* __restrict__ keys, const float* __restrict__ sp, const T* __restrict__ w, int ldw, int N,
+                     int C, int log2C, int K, T* __restrict__ dx, int ld_dx, float* __restrict__ part, int* __restrict__ rows_ws) {
+    constexpr int V = Chunk<T>::N;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);        // warp of the cloud: entries [32 wi, 32 wi + 32)
+    const int nw = C >> 5;
+    if (wi >= nw) return;
     const int chunks = K / V;                              // 16-byte chunks per row; lane owns chunks lane, lane + 32, ...
+    const unsigned* kb = keys + (long long)b * C + wi * 32;
+    const float* spb = sp + (long long)b * C;
     T* dxb = dx + (long long)b * N * ld_dx;
+    float* pw = part + ((long long)b * nw + wi) * 2 * K;
     float acc[KV][V];
 #pragma unroll
     for (int q = 0; q < KV; ++q)
@@ -134,12 +139,10 @@ pool_lin_sparse_dx_kernel(const float* __restrict__ sp, const int32_t* __restric
             const int ch = lane + 32 * q;
             if (ch < chunks) {
                 if (first || last) {
-                    float* ps = part_s + ((long long)wi * 2 + (first ? 0 : 1)) * K + ch * V;
+                    float* ps = pw + (first ? 0 : K) + ch * V;
 #pragma unroll
                     for (int i = 0; i < V; ++i) ps[i] = acc[q][i];
                 } else {
-                    // one add per element of this row in the whole kernel (single writer): order-independent, and the
-                    // warp does not wait for the row to come back
                     Chunk<T>::red_add(dxb + (long long)cur * ld_dx + ch * V, acc[q]);
                 }
             }
@@ -152,14 +155,14 @@ pool_lin_sparse_dx_kernel(const float* __restrict__ sp, const int32_t* __restric
     const unsigned cmask = (unsigned)C - 1u;
     for (int i0 = 0; i0 < 32; i0 += 8) {
         // eight entries per round: their W chunks are all requested before the first one is used
-        unsigned keys[8];
+        unsigned ks[8];
         float scs[8];
         uint4 raw[8][KV];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            keys[u] = key_s[wi * 32 + i0 + u];                               // broadcast read
-            const int c2 = keys[u] == 0xffffffffu ? 0 : (int)(keys[u] & cmask);
-            scs[u] = s_s[c2];
+            ks[u] = __ldg(kb + i0 + u);                                       // same address for the whole warp
+            const int c2 = ks[u] == 0xffffffffu ? 0 : (int)(ks[u] & cmask);
+            scs[u] = __ldg(spb + c2);
             const T* wr = w + (long long)c2 * ldw;
 #pragma unroll
             for (int q = 0; q < KV; ++q) {
@@ -169,8 +172,8 @@ pool_lin_sparse_dx_kernel(const float* __restrict__ sp, const int32_t* __restric
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (keys[u] != 0xffffffffu) {                                    // invalid entries sort last (warp-uniform)
-                const int row = (int)(keys[u] >> log2C);
+            if (ks[u] != 0xffffffffu) {                                      // invalid entries sort last (warp-uniform)
+                const int row = (int)(ks[u] >> log2C);
                 if (row != cur) { emit(false); cur = row; }
 #pragma unroll
                 for (int q = 0; q < KV; ++q) {
@@ -183,22 +186,43 @@ pool_lin_sparse_dx_kernel(const float* __restrict__ sp, const int32_t* __restric
         }
     }
     emit(true);
-    if (lane == 0) { rows_s[2 * wi] = head_row; rows_s[2 * wi + 1] = tail_row; }
+    if (lane == 0) {
+        rows_ws[((long long)b * nw + wi) * 2] = head_row;
+        rows_ws[((long long)b * nw + wi) * 2 + 1] = tail_row;
+    }
+}
+
+// merge the boundary runs of a cloud in warp order: thread = column pair (one add per element)
+template <typename T>
+__global__ void pool_lin_merge_kernel(const float* __restrict__ part, const int* __restrict__ rows_ws, int N, int C, int K,
+                                      T* __restrict__ dx, int ld_dx) {
+    extern __shared__ int mrows_s[];                                           // [2 nw]
+    const int b = blockIdx.x;
+    const int nw = C >> 5;
+    for (int i = threadIdx.x; i < 2 * nw; i += blockDim.x) mrows_s[i] = rows_ws[(long long)b * nw * 2 + i];
     __syncthreads();
-    // merge the boundary runs in warp order: thread = column pair (one add per element, as above)
-    for (int col = 2 * t; col < K; col += 2 * blockDim.x) {
+    const float* pb = part + (long long)b * nw * 2 * K;
+    T* dxb = dx + (long long)b * N * ld_dx;
+    for (int col = 2 * threadIdx.x; col < K; col += 2 * blockDim.x) {
         int r0 = -1;
         float v0 = 0.f, v1 = 0.f;
-        for (int q = 0; q < 2 * nw; ++q) {
-            const int r = rows_s[q];
-            if (r < 0) continue;
-            if (r != r0) {
-                if (r0 >= 0) red_add2(dxb + (long long)r0 * ld_dx + col, v0, v1);
-                r0 = r;
-                v0 = v1 = 0.f;
+        for (int q0 = 0; q0 < 2 * nw; q0 += 8) {       // 2 nw is a multiple of 8 (C >= 128) or smaller than 8 (C = 64)
+            float2 pv[8];                                // eight partials in flight (unused slots hold stale but valid memory)
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                pv[u] = q0 + u < 2 * nw ? *reinterpret_cast<const float2*>(pb + (long long)(q0 + u) * K + col) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = q0 + u < 2 * nw ? mrows_s[q0 + u] : -1;
+                if (r < 0) continue;
+                if (r != r0) {
+                    if (r0 >= 0) red_add2(dxb + (long long)r0 * ld_dx + col, v0, v1);
+                    r0 = r;
+                    v0 = v1 = 0.f;
+                }
+                v0 += pv[u].x;
+                v1 += pv[u].y;
             }
-            v0 += part_s[(long long)q * K + col];
-            v1 += part_s[(long long)q * K + col + 1];
         }
         if (r0 >= 0) red_add2(dxb + (long long)r0 * ld_dx + col, v0, v1);
     }
@@ -341,6 +365,32 @@ colsum_final_kernel(const float* __restrict__ partial, int G, int K, float* __re
     }
 }
 
+// ---- gradient bucket: up to 32 fp32 tensors copied into their slices of a flat buffer by ONE launch. The table of
+// (source, destination, element count) travels as a kernel parameter, so nothing is staged through device memory.
+struct MultiCopy {
+    const float* src[32];
+    float* dst[32];
+    unsigned first_chunk[33];       // prefix sums of the 1024-element chunk counts
+    unsigned count[32];
+    int n;
+};
+__global__ void __launch_bounds__(256)
+multi_copy_kernel(const __grid_constant__ MultiCopy t) {
+    const unsigned chunk = blockIdx.x;
+    int i = 0;
+#pragma unroll 1
+    while (i + 1 < t.n && chunk >= t.first_chunk[i + 1]) ++i;
+    const unsigned base = (chunk - t.first_chunk[i]) * 1024u;
+    const float* __restrict__ s = t.src[i];
+    float* __restrict__ d = t.dst[i];
+    const unsigned n = t.count[i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const unsigned e = base + q * 256u + threadIdx.x;
+        if (e < n) d[e] = __ldg(s + e);
+    }
+}
+
 // ---- feature table: [x1 | x2 | ...] (fp32, point-major) -> one (P, sum C_i) table in the compute dtype, and back
 struct CatSrc {
     const float* p[4];
@@ -350,35 +400,49 @@ struct CatSrc {
     int n;
 };
 
+// Both kernels keep two independent groups of loads in flight per thread (U = 2): with one 32-byte load per thread the
+// 75 MB pass ran at 3.5 TB/s.
 template <typename OT, int V>
 __global__ void __launch_bounds__(256)
 cat_cast_kernel(CatSrc s, unsigned rows, OT* __restrict__ out, int ld_out) {
+    constexpr int U = 2;
     const unsigned groups = (unsigned)s.c0[s.n] / V;
     const unsigned total = rows * groups;
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const unsigned r = e / groups;
-        const int col = (int)(e - r * groups) * V;
-        int i = 0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += U * stride) {
+        float f[U][V];
+        unsigned r[U];
+        int col[U];
 #pragma unroll
-        for (int t = 1; t < 4; ++t) i += (t < s.n && col >= s.c0[t]) ? 1 : 0;
-        const float* sp = s.p[i] + (long long)r * s.ld[i] + (col - s.c0[i]);
-        float f[V];
+        for (int u = 0; u < U; ++u) {
+            const unsigned e = e0 + u * stride < total ? e0 + u * stride : e0;
+            r[u] = e / groups;
+            col[u] = (int)(e - r[u] * groups) * V;
+            int i = 0;
 #pragma unroll
-        for (int q = 0; q < V / 4; ++q) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(sp) + q);
-            f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+            for (int t = 1; t < 4; ++t) i += (t < s.n && col[u] >= s.c0[t]) ? 1 : 0;
+            const float* sp = s.p[i] + (long long)r[u] * s.ld[i] + (col[u] - s.c0[i]);
+#pragma unroll
+            for (int q = 0; q < V / 4; ++q) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(sp) + q);
+                f[u][4 * q] = v.x; f[u][4 * q + 1] = v.y; f[u][4 * q + 2] = v.z; f[u][4 * q + 3] = v.w;
+            }
         }
-        OT* o = out + (long long)r * ld_out + col;
-        if (sizeof(OT) == 2) {
-            __nv_bfloat162 h[V / 2];
 #pragma unroll
-            for (int q = 0; q < V / 2; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-            if (V == 8) *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
-            else *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(h);
-        } else {
+        for (int u = 0; u < U; ++u) {
+            if (u > 0 && e0 + u * stride >= total) break;
+            OT* o = out + (long long)r[u] * ld_out + col[u];
+            if (sizeof(OT) == 2) {
+                __nv_bfloat162 h[V / 2];
 #pragma unroll
-            for (int q = 0; q < V / 4; ++q)
-                reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                for (int q = 0; q < V / 2; ++q) h[q] = __floats2bfloat162_rn(f[u][2 * q], f[u][2 * q + 1]);
+                if (V == 8) *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
+                else *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(h);
+            } else {
+#pragma unroll
+                for (int q = 0; q < V / 4; ++q)
+                    reinterpret_cast<float4*>(o)[q] = make_float4(f[u][4 * q], f[u][4 * q + 1], f[u][4 * q + 2], f[u][4 * q + 3]);
+            }
         }
     }
 }
@@ -386,37 +450,49 @@ cat_cast_kernel(CatSrc s, unsigned rows, OT* __restrict__ out, int ld_out) {
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
 split_cast_kernel(CatSrc s, unsigned rows, const T* __restrict__ g, int ld_g) {
+    constexpr int U = 2;
     const unsigned groups = (unsigned)s.c0[s.n] / V;
     const unsigned total = rows * groups;
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const unsigned r = e / groups;
-        const int col = (int)(e - r * groups) * V;
-        int i = 0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += U * stride) {
+        float f[U][V];
+        unsigned r[U];
+        int col[U];
 #pragma unroll
-        for (int t = 1; t < 4; ++t) i += (t < s.n && col >= s.c0[t]) ? 1 : 0;
-        const T* gp = g + (long long)r * ld_g + col;
-        float f[V];
-        if (sizeof(T) == 2) {
-            if (V == 8) {
-                const uint4 pk = __ldg(reinterpret_cast<const uint4*>(gp));
-                fs_bf16x8_to_float(pk, f);
+        for (int u = 0; u < U; ++u) {
+            const unsigned e = e0 + u * stride < total ? e0 + u * stride : e0;
+            r[u] = e / groups;
+            col[u] = (int)(e - r[u] * groups) * V;
+            const T* gp = g + (long long)r[u] * ld_g + col[u];
+            if (sizeof(T) == 2) {
+                if (V == 8) {
+                    const uint4 pk = __ldg(reinterpret_cast<const uint4*>(gp));
+                    fs_bf16x8_to_float(pk, f[u]);
+                } else {
+                    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(gp));
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+                    const float2 lo = __bfloat1622float2(h[0]), hi = __bfloat1622float2(h[1]);
+                    f[u][0] = lo.x; f[u][1] = lo.y; f[u][2] = hi.x; f[u][3] = hi.y;
+                }
             } else {
-                const uint2 pk = __ldg(reinterpret_cast<const uint2*>(gp));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-                const float2 lo = __bfloat1622float2(h[0]), hi = __bfloat1622float2(h[1]);
-                f[0] = lo.x; f[1] = lo.y; f[2] = hi.x; f[3] = hi.y;
-            }
-        } else {
 #pragma unroll
-            for (int q = 0; q < V / 4; ++q) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(gp) + q);
-                f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+                for (int q = 0; q < V / 4; ++q) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(gp) + q);
+                    f[u][4 * q] = v.x; f[u][4 * q + 1] = v.y; f[u][4 * q + 2] = v.z; f[u][4 * q + 3] = v.w;
+                }
             }
         }
-        float* o = s.q[i] + (long long)r * s.ld[i] + (col - s.c0[i]);
 #pragma unroll
-        for (int q = 0; q < V / 4; ++q)
-            reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        for (int u = 0; u < U; ++u) {
+            if (u > 0 && e0 + u * stride >= total) break;
+            int i = 0;
+#pragma unroll
+            for (int t = 1; t < 4; ++t) i += (t < s.n && col[u] >= s.c0[t]) ? 1 : 0;
+            float* o = s.q[i] + (long long)r[u] * s.ld[i] + (col[u] - s.c0[i]);
+#pragma unroll
+            for (int q = 0; q < V / 4; ++q)
+                reinterpret_cast<float4*>(o)[q] = make_float4(f[u][4 * q], f[u][4 * q + 1], f[u][4 * q + 2], f[u][4 * q + 3]);
+        }
     }
 }
 
@@ -453,22 +529,30 @@ extern "C" int fs_pool_lin_bwd_prep(int device, fs_stream_t stream_, const float
 }
 
 namespace {
-// KV = 16-byte chunks per lane: K * sizeof(T) / 16 chunks over 32 lanes
+// KV = 16-byte chunks per lane: K * sizeof(T) / 16 chunks over 32 lanes. ws: keys [B, C] u32 | rows [B, C/32, 2] i32 |
+// partials [B, C/32, 2, K] f32
+size_t sparse_dx_ws_bytes(int B, int C, int K) {
+    return (size_t)B * C * 4 + (size_t)B * (C / 32) * 2 * 4 + (size_t)B * (C / 32) * 2 * K * 4;
+}
 template <typename T>
 int launch_sparse_dx(cudaStream_t stream, const float* sp, const int32_t* arg, const T* w, int ldw, int B, int N, int C, int K,
-                     T* dx, int ld_dx) {
+                     T* dx, int ld_dx, void* ws) {
     int log2C = 0;
     while ((1 << log2C) < C) ++log2C;
     const int nw = C / 32;
-    const size_t smem = (size_t)C * 8 + (size_t)nw * 2 * 4 + (size_t)nw * 2 * K * 4;
+    unsigned* keys = (unsigned*)ws;
+    int* rows_ws = (int*)(keys + (size_t)B * C);
+    float* part = (float*)(rows_ws + (size_t)B * nw * 2);
+    pool_lin_sort_kernel<<<B, C, (size_t)C * 4, stream>>>(arg, N, C, log2C, keys);
     const int kv = (K / Chunk<T>::N + 31) / 32;
-#define GO(KV)                                                                                                              \
-    do {                                                                                                                    \
-        FS_CUDA_TRY(cudaFuncSetAttribute(pool_lin_sparse_dx_kernel<T, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        pool_lin_sparse_dx_kernel<T, KV><<<B, C, smem, stream>>>(sp, arg, w, ldw, N, C, log2C, K, dx, ld_dx);                \
-    } while (0)
-    if (kv == 1) GO(1); else if (kv == 2) GO(2); else if (kv <= 4) GO(4); else return FS_ERR_UNSUPPORTED;
-#undef GO
+    const dim3 grid((nw + 3) / 4, B);
+    if (kv == 1) pool_lin_rows_kernel<T, 1><<<grid, 128, 0, stream>>>(keys, sp, w, ldw, N, C, log2C, K, dx, ld_dx, part, rows_ws);
+    else if (kv == 2) pool_lin_rows_kernel<T, 2><<<grid, 128, 0, stream>>>(keys, sp, w, ldw, N, C, log2C, K, dx, ld_dx, part, rows_ws);
+    else if (kv <= 4) pool_lin_rows_kernel<T, 4><<<grid, 128, 0, stream>>>(keys, sp, w, ldw, N, C, log2C, K, dx, ld_dx, part, rows_ws);
+    else return FS_ERR_UNSUPPORTED;
+    int mt = (K / 2 + 31) / 32 * 32;
+    if (mt > 256) mt = 256;
+    pool_lin_merge_kernel<T><<<B, mt, (size_t)2 * nw * 4, stream>>>(part, rows_ws, N, C, K, dx, ld_dx);
     return FS_OK;
 }
 template <typename T>
@@ -484,18 +568,23 @@ int launch_dw(cudaStream_t stream, const float* sp, const int32_t* arg, const T*
 }
 }  // namespace
 
+extern "C" size_t fs_pool_lin_bwd_ws_bytes(int B, int C, int K) {
+    if (B <= 0 || C <= 0 || K <= 0) return 0;
+    return sparse_dx_ws_bytes(B, C, K);
+}
+
 extern "C" int fs_pool_lin_bwd_dx_sparse(int device, fs_stream_t stream_, const float* sp, const int32_t* arg, const void* w,
-                                         int dtype, int ldw, int B, int N, int C, int K, void* dx, int ld_dx) {
-    if (!sp || !arg || !w || !dx || B <= 0 || N <= 0 || C <= 0 || ldw < K || ld_dx < K) return FS_ERR_BAD_ARG;
+                                         int dtype, int ldw, int B, int N, int C, int K, void* dx, int ld_dx, void* ws) {
+    if (!sp || !arg || !w || !dx || !ws || B <= 0 || N <= 0 || C <= 0 || ldw < K || ld_dx < K) return FS_ERR_BAD_ARG;
     const int V = dtype == FS_BF16 ? 8 : 4;
     if (K % V || K > 512 || ldw % V || ld_dx % V || C < 32 || C > 1024 || (C & (C - 1)) || (long long)N * C >= (1ll << 32) - 1 ||
-        ((uintptr_t)w & 15) || ((uintptr_t)dx & 15))
+        B > 65535 || ((uintptr_t)w & 15) || ((uintptr_t)dx & 15) || ((uintptr_t)ws & 15))
         return FS_ERR_UNSUPPORTED;
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int rc = dtype == FS_BF16
-        ? launch_sparse_dx(stream, sp, arg, (const __nv_bfloat16*)w, ldw, B, N, C, K, (__nv_bfloat16*)dx, ld_dx)
-        : launch_sparse_dx(stream, sp, arg, (const float*)w, ldw, B, N, C, K, (float*)dx, ld_dx);
+        ? launch_sparse_dx(stream, sp, arg, (const __nv_bfloat16*)w, ldw, B, N, C, K, (__nv_bfloat16*)dx, ld_dx, ws)
+        : launch_sparse_dx(stream, sp, arg, (const float*)w, ldw, B, N, C, K, (float*)dx, ld_dx, ws);
     if (rc != FS_OK) return rc;
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
@@ -589,5 +678,32 @@ extern "C" int fs_split_cast(int device, fs_stream_t stream_, int n, void* const
         else split_cast_kernel<float, 4><<<grid, 256, 0, stream>>>(s, (unsigned)rows, (const float*)g, ld_g);
     }
     FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_multi_copy_f32(int device, fs_stream_t stream_, int n, const void* const* srcs, void* const* dsts,
+                                 const long long* counts) {
+    if (n < 0 || (n > 0 && (!srcs || !dsts || !counts))) return FS_ERR_BAD_ARG;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        MultiCopy t;
+        t.n = n - i0 < 32 ? n - i0 : 32;
+        unsigned chunks = 0;
+        for (int i = 0; i < t.n; ++i) {
+            const long long c = counts[i0 + i];
+            if (c < 0 || c >= (1ll << 31) || (c > 0 && (!srcs[i0 + i] || !dsts[i0 + i]))) return FS_ERR_BAD_ARG;
+            t.src[i] = (const float*)srcs[i0 + i];
+            t.dst[i] = (float*)dsts[i0 + i];
+            t.count[i] = (unsigned)c;
+            t.first_chunk[i] = chunks;
+            chunks += (unsigned)((c + 1023) / 1024);
+        }
+        t.first_chunk[t.n] = chunks;
+        for (int i = t.n; i < 32; ++i) { t.src[i] = nullptr; t.dst[i] = nullptr; t.count[i] = 0; t.first_chunk[i + 1] = chunks; }
+        if (chunks == 0) continue;
+        multi_copy_kernel<<<chunks, 256, 0, stream>>>(t);
+        FS_RETURN_IF_LAUNCH_FAILED();
+    }
     return FS_OK;
 }

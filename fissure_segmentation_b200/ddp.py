@@ -7,6 +7,8 @@ last gradient of a bucket has been accumulated, an asynchronous all-reduce (NCCL
 gloo in the CPU tests) is issued on that bucket while the rest of backward is still running. BatchNorm
 statistics stay per rank (standard DDP semantics).
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -81,7 +83,17 @@ class FlatDataParallel:
         if missing:                 # parameters without a gradient this step count as zero
             self.flat_grad[s:e].zero_()
         if src:
-            torch._foreach_copy_(dst, src)
+            fast = all(g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() for g in src) and \
+                self.flat_grad.dtype == torch.float32
+            if fast:
+                # one launch for the whole bucket (the multi-tensor ATen copy takes ~17 us per bucket of ~15 tensors)
+                n = len(src)
+                sp = (ctypes.c_void_p * n)(*[g.data_ptr() for g in src])
+                dp = (ctypes.c_void_p * n)(*[d.data_ptr() for d in dst])
+                cn = (ctypes.c_longlong * n)(*[g.numel() for g in src])
+                _lib.call("fs_multi_copy_f32", self.flat_grad, n, sp, dp, cn)
+            else:
+                torch._foreach_copy_(dst, src)
         for i in self._bucket_members[b]:
             if self.params[i].grad is not None:
                 self.params[i].grad = self._grad_views[i]          # .grad shows the (to be) reduced gradient

@@ -631,8 +631,9 @@ class _PoolLinearFn(torch.autograd.Function):
         elif ctx.needs_input_grad[0]:
             dx = torch.zeros_like(x)
         if dx is not None:
+            ws = _workspace(_lib.load().fs_pool_lin_bwd_ws_bytes(B, C, K), dev, "pool_lin")
             _lib.call("fs_pool_lin_bwd_dx_sparse", x, sp, arg, wc, _lib.dtype_code(wc), wc.stride(0), B, N, C, K, dx,
-                      dx.stride(0))
+                      dx.stride(0), ws)
         if ctx.needs_input_grad[1]:
             dw = torch.empty(C, K, dtype=torch.float32, device=dev)
             _lib.call("fs_pool_lin_bwd_dw", x, sp, arg, x, _lib.dtype_code(x), x.stride(0), B, N, C, K,

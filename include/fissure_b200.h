@@ -328,8 +328,9 @@ int fs_pool_bwd(int device, fs_stream_t stream, const void* x, int dtype, int ld
  *   fs_pool_lin_bwd_prep       a [C], bvec [C], sp [B,C] = scale * g * LeakyReLU'(z_sel) from g [B,C], sel [B,C],
  *                              coef [4C] (fs_bn_finalize layout) and dgb [2C] (double; fs_bn_act_bwd on the B x C
  *                              selected values)
- *   fs_pool_lin_bwd_dx_sparse  dx[b*N + arg[b,c], :] += sp[b,c] * w[c, :]   (w [C,K], dx [B*N,K], same dtype; every
- *                              row has one writer and a fixed summation order: deterministic, no atomics)
+ *   fs_pool_lin_bwd_dx_sparse  dx[b*N + arg[b,c], :] += sp[b,c] * w[c, :]   (w [C,K], dx [B*N,K], same dtype; C a power of
+ *                              two <= 1024; every element receives ONE add of a sum formed in a fixed order:
+ *                              deterministic; three launches: per-cloud sort, row sums, boundary merge)
  *   fs_pool_lin_bwd_dw         dw [C,K] f32 = S^T X + a colsum^T + diag(bvec) wg  (a / bvec / colsum / wg nullable:
  *                              eval-mode statistics have no dense part); K % 32 == 0, K <= 512
  */
@@ -341,8 +342,10 @@ int fs_colsum(int device, fs_stream_t stream, const void* x, int dtype, int ld, 
 int fs_pool_lin_bwd_prep(int device, fs_stream_t stream, const float* g, const float* sel, const float* coef,
                          float slope, const double* dgb, double count, int train_stats, int B, int C, float* a,
                          float* bvec, float* sp);
+size_t fs_pool_lin_bwd_ws_bytes(int B, int C, int K);
 int fs_pool_lin_bwd_dx_sparse(int device, fs_stream_t stream, const float* sp, const int32_t* arg, const void* w,
-                              int dtype, int ldw, int B, int N, int C, int K, void* dx, int ld_dx);
+                              int dtype, int ldw, int B, int N, int C, int K, void* dx, int ld_dx,
+                              void* ws /* fs_pool_lin_bwd_ws_bytes(B, C, K) bytes, 16-byte aligned */);
 int fs_pool_lin_bwd_dw(int device, fs_stream_t stream, const float* sp, const int32_t* arg, const void* x, int dtype,
                        int ldx, int B, int N, int C, int K, const float* a, const float* bvec, const float* colsum,
                        const float* wg, float* dw);
@@ -356,6 +359,13 @@ int fs_cat_cast(int device, fs_stream_t stream, int n, const void* const* srcs, 
                 long long rows, void* out, int out_dtype, int ld_out);
 int fs_split_cast(int device, fs_stream_t stream, int n, void* const* dsts, const int* widths, const int* lds,
                   long long rows, const void* g, int g_dtype, int ld_g);
+
+/*
+ * Gradient bucket -> flat buffer (ddp.py): dsts[i][0..counts[i]) = srcs[i][...] for n fp32 tensors in one launch per 32
+ * tensors; srcs / dsts / counts are HOST arrays (the table is passed to the kernel by value).
+ */
+int fs_multi_copy_f32(int device, fs_stream_t stream, int n, const void* const* srcs, void* const* dsts,
+                      const long long* counts);
 
 /* ---------------------------------------------------------------- Chamfer ------------------ */
 
