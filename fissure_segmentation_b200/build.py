@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfissure_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["knn.cu", "knn_tc.cu", "edgeconv.cu", "edgeconv_smem.cu", "edge3.cu", "edge2.cu", "dense.cu", "heads.cu", "chamfer.cu", "pointops.cu", "infer.cu", "microbench.cu"]
+SOURCES = ["knn.cu", "knn_tc.cu", "edgeconv.cu", "edgeconv_smem.cu", "edge3.cu", "edge2.cu", "dense.cu", "heads.cu", "pool_gemm.cu", "chamfer.cu", "pointops.cu", "infer.cu", "microbench.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

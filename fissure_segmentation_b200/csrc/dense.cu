@@ -535,3 +535,15 @@ extern "C" int fs_pool_bwd(int device, fs_stream_t stream_, const void* x, int d
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
 }
+
+// sel / arg from the packed (ordered key << 32 | ~row) table that fs_pool_reduce and fs_pool_gemm fill
+extern "C" int fs_pool_decode(int device, fs_stream_t stream_, const unsigned long long* packed, const float* gamma, int B, int C,
+                              float* sel, int32_t* arg) {
+    if (!packed || !gamma || !sel || !arg || B <= 0 || C <= 0) return FS_ERR_BAD_ARG;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long total = (long long)B * C;
+    pool_decode_kernel<<<fs_div_up(total, 256), 256, 0, stream>>>(packed, gamma, C, total, sel, arg);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}

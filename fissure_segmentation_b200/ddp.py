@@ -16,7 +16,7 @@ from . import _lib
 
 
 class FlatDataParallel:
-    def __init__(self, module, n_buckets=2, process_group=None, broadcast=True):
+    def __init__(self, module, n_buckets=2, process_group=None, broadcast=True, tail_share=None):
         self.module = module
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -42,9 +42,15 @@ class FlatDataParallel:
                 self._slices.append((off, n))
                 off += n
         self.params = order
-        # contiguous buckets of roughly equal size
+        # contiguous buckets of roughly equal size; with tail_share the LAST bucket (the gradients backward produces
+        # last - its all-reduce is the only one nothing can overlap) holds about that fraction of the parameters and
+        # the others share the rest: a small tail keeps the exposed collective latency-bound instead of size-bound
         n_buckets = max(1, min(n_buckets, len(order)))
-        target = total / n_buckets
+        if tail_share is not None and n_buckets > 1:
+            head = total * (1.0 - float(tail_share)) / (n_buckets - 1)
+            targets = [head] * (n_buckets - 1) + [total]
+        else:
+            targets = [total / n_buckets] * n_buckets
         self.buckets = []          # (start, end, n_params)
         self._bucket_members = []  # parameter positions of every bucket
         self._bucket_of = {}
@@ -53,6 +59,7 @@ class FlatDataParallel:
             self._bucket_of[id(order[i])] = b
             count += 1
             end = o + n
+            target = targets[b]
             if (end - start >= target and b < n_buckets - 1) or i == len(order) - 1:
                 self.buckets.append((start, end, count))
                 self._bucket_members.append(list(range(first, i + 1)))

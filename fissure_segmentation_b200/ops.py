@@ -574,36 +574,67 @@ def _gram_f32(x):
     return torch.mm(x.t(), x, out_dtype=torch.float32)
 
 
+USE_POOL_GEMM = os.environ.get("FS_POOL_GEMM", "1") != "0"
+
+
+def _colsum_f32(x):
+    rows, K = x.shape
+    out = torch.empty(K, dtype=torch.float32, device=x.device)
+    partial = _workspace(4 * K * _lib.load().fs_colsum_partials(), x.device, "colsum")
+    _lib.call("fs_colsum", x, x, _lib.dtype_code(x), x.stride(0), rows, K, partial, out)
+    return out
+
+
 class _PoolLinearFn(torch.autograd.Function):
     """out (B, C) = max over the N rows of each cloud of LeakyReLU(BatchNorm(X W^T)): Conv1d + BN + LeakyReLU +
-    AdaptiveMaxPool1d of the global feature (models/dgcnn.py:123-126, 156). Forward: library GEMM, then one pass that
-    keeps only per-cloud max/min + statistics (the activation is never written and the GEMM output is NOT kept for
-    backward). Backward: dy = S + a + b*y with one non-zero of S per (cloud, channel), so with y = X W^T
+    AdaptiveMaxPool1d of the global feature (models/dgcnn.py:123-126, 156).
+
+    Forward, bf16 tables with K in {64, 128, 192}: ONE tcgen05 kernel forms the product tile by tile in TMEM and keeps
+    only per-cloud max/min + arg (csrc/pool_gemm.cu) - the (B*N, C) product is never written; the BatchNorm sums come from
+    the Gram matrix (sum y = W colsum(X), sum y^2 = diag(W X^T X W^T)). Otherwise: library GEMM, then one pass that keeps
+    max/min + statistics. Either way nothing of size B*N x C is kept for backward.
+    Backward: dy = S + a + b*y with one non-zero of S per (cloud, channel), so with y = X W^T
         dX = S W + 1 (a^T W) + X (W^T diag(b) W),      dW = S^T X + a colsum(X)^T + diag(b) W (X^T X)
     - K x K products instead of the P x C gradient (csrc/heads.cu)."""
 
     @staticmethod
     def forward(ctx, x, w, gamma, beta, running_mean, running_var, nbt, training, eps, momentum, slope, B, N):
         wc = w.detach().to(x.dtype).contiguous()              # (C, K)
-        C = wc.shape[0]
+        C, K = wc.shape
         dev = x.device
-        y = x @ wc.t()
+        lib = _lib.load()
         gamma32, beta32 = gamma.detach().float(), beta.detach().float()
         sel = torch.empty(B, C, dtype=torch.float32, device=dev)
         arg = torch.empty(B, C, dtype=torch.int32, device=dev)
         stats = _stats_buffer(C, dev) if training else None
         packed = _zeros64(B * C, dev).view(torch.int64)
-        _lib.call("fs_pool_reduce", y, y, _lib.dtype_code(y), y.stride(0), B, N, C, gamma32, sel, arg, stats, packed)
-        coef = _bn_coef(y, stats, B * N, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
+        colsum = wg = None
+        fused = (USE_POOL_GEMM and x.dtype == torch.bfloat16 and lib.fs_pool_gemm_supported(B, N, C, K)
+                 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0)
+        if fused:
+            if training:
+                with _matmul_tf32(False):
+                    colsum = _colsum_f32(x)
+                    wg = (wc.float() @ _gram_f32(x)).contiguous()                    # W (X^T X)       (C, K)
+                _lib.call("fs_pool_stats_from_gram", x, wc, _lib.dtype_code(wc), wc.stride(0), wg, colsum, C, K, stats)
+            w_signed = wc * torch.where(gamma32 >= 0, 1.0, -1.0).to(wc.dtype).unsqueeze(1)
+            _lib.call("fs_pool_gemm", x, x, x.stride(0), w_signed, B, N, C, K, packed)
+            _lib.call("fs_pool_decode", x, packed, gamma32, B, C, sel, arg)
+            ref = x
+        else:
+            y = x @ wc.t()
+            _lib.call("fs_pool_reduce", y, y, _lib.dtype_code(y), y.stride(0), B, N, C, gamma32, sel, arg, stats, packed)
+            ref = y
+        coef = _bn_coef(ref, stats, B * N, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
         out = torch.empty(B, C, dtype=x.dtype, device=dev)
-        _lib.call("fs_bn_act_apply", y, sel, 0, C, B, C, None, 1, coef, float(slope), out, _lib.dtype_code(out), C)
-        ctx.save_for_backward(x, wc, sel, arg, coef)
+        _lib.call("fs_bn_act_apply", x, sel, 0, C, B, C, None, 1, coef, float(slope), out, _lib.dtype_code(out), C)
+        ctx.save_for_backward(x, wc, sel, arg, coef, colsum, wg)
         ctx.training, ctx.slope, ctx.B, ctx.N, ctx.w_dtype = training, slope, B, N, w.dtype
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, wc, sel, arg, coef = ctx.saved_tensors
+        x, wc, sel, arg, coef, colsum, wg = ctx.saved_tensors
         B, N, C, K = ctx.B, ctx.N, wc.shape[0], wc.shape[1]
         dev = x.device
         g32 = g.float().contiguous()
@@ -616,17 +647,14 @@ class _PoolLinearFn(torch.autograd.Function):
                   a, bvec, sp)
         w32 = wc.float()
         dx = dw = None
-        colsum = wg = None
         if ctx.training:
             with _matmul_tf32(False):     # the K x K factors carry a covariance (cancellation): full fp32 products
                 if ctx.needs_input_grad[0]:
                     m = (w32 * bvec.unsqueeze(1)).t() @ w32                              # W^T diag(b) W   (K, K)
                     r = a @ w32                                                          # a^T W           (K,)
                     dx = torch.addmm(r.to(x.dtype), x, m.to(x.dtype))
-                if ctx.needs_input_grad[1]:
-                    colsum = torch.empty(K, dtype=torch.float32, device=dev)
-                    partial = _workspace(4 * K * _lib.load().fs_colsum_partials(), dev, "colsum")
-                    _lib.call("fs_colsum", x, x, _lib.dtype_code(x), x.stride(0), B * N, K, partial, colsum)
+                if ctx.needs_input_grad[1] and wg is None:
+                    colsum = _colsum_f32(x)
                     wg = (w32 @ _gram_f32(x)).contiguous()                               # W (X^T X)       (C, K)
         elif ctx.needs_input_grad[0]:
             dx = torch.zeros_like(x)
@@ -636,8 +664,9 @@ class _PoolLinearFn(torch.autograd.Function):
                       dx.stride(0), ws)
         if ctx.needs_input_grad[1]:
             dw = torch.empty(C, K, dtype=torch.float32, device=dev)
+            tr = ctx.training
             _lib.call("fs_pool_lin_bwd_dw", x, sp, arg, x, _lib.dtype_code(x), x.stride(0), B, N, C, K,
-                      a if ctx.training else None, bvec if ctx.training else None, colsum, wg, dw)
+                      a if tr else None, bvec if tr else None, colsum if tr else None, wg if tr else None, dw)
             dw = dw.to(ctx.w_dtype)
         dgb32 = dgb[:2 * C].float()
         return dx, dw, dgb32[C:], dgb32[:C], None, None, None, None, None, None, None, None, None

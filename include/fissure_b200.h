@@ -334,6 +334,23 @@ int fs_pool_bwd(int device, fs_stream_t stream, const void* x, int dtype, int ld
  *   fs_pool_lin_bwd_dw         dw [C,K] f32 = S^T X + a colsum^T + diag(bvec) wg  (a / bvec / colsum / wg nullable:
  *                              eval-mode statistics have no dense part); K % 32 == 0, K <= 512
  */
+/*
+ * Global feature forward on tcgen05 (csrc/pool_gemm.cu): packed[b,c] = max over the N rows of cloud b of
+ * (x w_signed^T)[., c] with its row, encoded (ordered key << 32) | ~row like fs_pool_reduce; the [B*N, C] product is never
+ * written. x [B*N, K] bf16 (row pitch ldx elements, 16-byte aligned rows), w_signed [C, K] bf16 contiguous = sign(gamma) * W
+ * (gamma >= 0 counts as +), packed [B*C] zero-filled. Supported: K in {64, 128, 192}, C % 128 == 0 (fs_pool_gemm_supported).
+ *   fs_pool_decode            sel [B,C] f32 (sign restored), arg [B,C] i32 (row within the cloud, -1: no finite value)
+ *   fs_pool_stats_from_gram   BatchNorm sums of the product without the product: stats[0:C] = W colsum(X),
+ *                             stats[C:2C] = rowwise (W G) . W, G = X^T X (fs_colstats layout, pivot 0); wg = W G [C,K] f32
+ */
+int fs_pool_gemm_supported(int B, int N, int C, int K);
+int fs_pool_gemm(int device, fs_stream_t stream, const void* x, int ldx, const void* w_signed, int B, int N, int C, int K,
+                 unsigned long long* packed);
+int fs_pool_decode(int device, fs_stream_t stream, const unsigned long long* packed, const float* gamma, int B, int C,
+                   float* sel, int32_t* arg);
+int fs_pool_stats_from_gram(int device, fs_stream_t stream, const void* w, int dtype, int ldw, const float* wg,
+                            const float* colsum, int C, int K, double* stats);
+
 /* Column sums of x [rows, K] (fp32 or bf16; K % 8 == 0 (bf16) / % 4 (fp32), 16-byte aligned rows) -> out [K] f32, through
  * fs_colsum_partials() x K fp32 partials in partial_ws (fixed chunking: deterministic). */
 int fs_colsum_partials(void);
