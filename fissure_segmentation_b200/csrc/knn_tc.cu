@@ -578,9 +578,14 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
         float gm[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) gm[e] = INFINITY;
+        // One 128-slot survivor list per query row, filled from both ends: the warp of column half 0 appends upwards from
+        // slot 0, the warp of half 1 downwards from the last slot, so a row overflows only when BOTH halves together exceed
+        // the list. (With 64 slots per half a Morton-sorted cloud overflowed ~1 % of the rows at k = 40 - the survivors of
+        // a row are runs of consecutive indices, i.e. whole 32-column blocks, and two of three blocks belong to one half -
+        // and every such row costs a pass of the exact kernel.)
         int cnt = 0;
-        int32_t* const out_j = cand_j + (cloud0 + (row_ok ? qrow : 0)) * TC_CAP + cb * (TC_CAP / TC_HALVES);
-        float* const out_d = cand_d + (cloud0 + (row_ok ? qrow : 0)) * TC_CAP + cb * (TC_CAP / TC_HALVES);
+        int32_t* const out_j = cand_j + (cloud0 + (row_ok ? qrow : 0)) * TC_CAP;
+        float* const out_d = cand_d + (cloud0 + (row_ok ? qrow : 0)) * TC_CAP;
         const int diag_jb = diag_zero ? q_row0 + w4 * 32 : -1;       // candidate block that holds this warp's diagonal
         int a = 0, jb = cb * 32;
         uint32_t ph = 0;
@@ -694,9 +699,10 @@ knn_tc_select_kernel(const __half* __restrict__ a_rows, long long P, const __gri
                         const int e = __ffs(hits) - 1;
                         hits &= hits - 1;
                         const float dv = stage[(((e >> 2) ^ (lane & 7)) << 2) + (e & 3)];
-                        if (cnt < TC_CAP / TC_HALVES) {
-                            out_j[cnt] = jb + e;
-                            out_d[cnt] = dv;
+                        if (cnt < TC_CAP) {          // a collision with the other end implies n0 + n1 > TC_CAP: the row is redone
+                            const int pos = cb ? TC_CAP - 1 - cnt : cnt;
+                            out_j[pos] = jb + e;
+                            out_d[pos] = dv;
                         }
                         ++cnt;
                     }
@@ -761,8 +767,8 @@ __device__ __forceinline__ void tc_finalize_row(const Exact& exact, long long cl
     const int lane = threadIdx.x & 31;
     float sd[H];
     int sj[H];
-    // survivors of the two column halves sit in [0, n0) and [TC_CAP/2, TC_CAP/2 + n - n0)
-    auto phys = [&](int slot) { return slot < n0 ? slot : TC_CAP / TC_HALVES + slot - n0; };
+    // survivors of the two column halves sit in [0, n0) and, filled downwards, in (TC_CAP - 1 - (n - n0), TC_CAP - 1]
+    auto phys = [&](int slot) { return slot < n0 ? slot : TC_CAP - 1 - (slot - n0); };
     {
         unsigned long long key[H];
 #pragma unroll
@@ -884,10 +890,10 @@ knn_tc_finalize_kernel(const float* __restrict__ x, int ldx, const float4* __res
     float e, g;
     tc_row_err(sh, __ldg(cnorm + row), cmax, qq, rmax, amax, e, g);
     const float Trow = __ldg(row_T + row);
-    // overflow of a half's list, too few survivors, or a cloud with NaN / Inf (amax, the norms and with them e, g and
+    // overflow of the row's list, too few survivors, or a cloud with NaN / Inf (amax, the norms and with them e, g and
     // T are then not finite): the exact kernel redoes this query
     const bool finite = (e + g + Trow + amax) < INFINITY;          // false for NaN and Inf
-    if (n0 > TC_CAP / TC_HALVES || n1 > TC_CAP / TC_HALVES || n < kk || !finite) {
+    if (n > TC_CAP || n < kk || !finite) {
         if (lane == 0) redo[row] = 1;
         return;
     }

@@ -7,9 +7,17 @@ from fissure_segmentation_b200.ddp import FlatAdam, FlatDataParallel
 from torch.profiler import profile, ProfilerActivity
 dev = 'cuda'
 torch.manual_seed(0)
-model = fs.DGCNNSeg(k=20, in_features=3, num_classes=4).to(dev); model.precision = "bf16"; model.train()
+import os
+CFG = os.environ.get("TRACE_CFG", "train")
+if CFG == "configC":
+    Bt, Nt, kt, Ct, dyn = 1, 8192, 40, 9, False
+elif CFG == "static40":
+    Bt, Nt, kt, Ct, dyn = 32, 2048, 40, 3, False
+else:
+    Bt, Nt, kt, Ct, dyn = 32, 2048, 20, 3, True
+model = fs.DGCNNSeg(k=kt, in_features=Ct, num_classes=4, dynamic=dyn).to(dev); model.precision = "bf16"; model.train()
 dp = FlatDataParallel(model, n_buckets=2); opt = FlatAdam(dp, lr=1e-3, weight_decay=1e-5)
-x, y = synth.make_batch(32, 2048, seed=1234); x, y = x.to(dev), y.to(dev)
+x, y = synth.make_batch(Bt, Nt, seed=1234, n_features=Ct - 3); x, y = x.to(dev), y.to(dev)
 def step():
     dp.zero_grad(); loss = F.cross_entropy(dp(x), y); loss.backward(); dp.finish_backward(); opt.step()
 for _ in range(3): step()
