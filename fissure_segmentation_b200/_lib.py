@@ -95,7 +95,7 @@ def _ptr(x):
 
 # kernels launched per entry point (for bench.py's gpu_launches claim)
 _LAUNCHES = {"fs_knn_feat": 2, "fs_knn_feat_tc": 5, "fs_knn3d_tc": 5, "fs_edge2_fwd": 2, "fs_edge2_bwd": 3, "fs_edge3_bn_coef": 2, "fs_edge3_bwd": 2, "fs_bn_act_bwd": 2,
-             "fs_pool_reduce": 2, "fs_colsum": 2, "fs_pool_lin_bwd_dx_sparse": 3}
+             "fs_pool_reduce": 2, "fs_colsum": 2, "fs_pool_lin_bwd_dx_sparse": 3, "fs_reverse_graph": 3}
 launch_count = 0          # kernels of this library launched so far in this process
 timed = {}                # name -> list of (start_event, end_event); filled only for names in `time_calls`
 time_calls = set()

@@ -193,7 +193,9 @@ int fs_edgeconv_fused_eval(int device, fs_stream_t stream, const void* table, in
 
 /*
  * Reverse (incoming-edge) graph of a kNN graph, per cloud: counting sort of the B*N*k edges by
- * target. rev_ptr [B*N+1] global exclusive offsets; rev_src [B*N*k] global source rows.
+ * target. rev_ptr [B*N+1] global exclusive offsets; rev_src [B*N*k] global source rows (order inside a
+ * target's list unspecified). Every idx entry must be a valid row of its cloud (0 <= idx < N), as the kNN
+ * entry points produce them; three small launches (histogram, per-cloud scan, fill).
  */
 int fs_reverse_graph(int device, fs_stream_t stream, const int32_t* idx, int B, int N, int k,
                      int32_t* rev_ptr, int32_t* rev_src);

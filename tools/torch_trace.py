@@ -10,7 +10,7 @@ torch.manual_seed(0)
 import os
 CFG = os.environ.get("TRACE_CFG", "train")
 if CFG == "configC":
-    Bt, Nt, kt, Ct, dyn = 1, 8192, 40, 9, False
+    Bt, Nt, kt, Ct, dyn = 8, 8192, 40, 9, False
 elif CFG == "static40":
     Bt, Nt, kt, Ct, dyn = 32, 2048, 40, 3, False
 else:
