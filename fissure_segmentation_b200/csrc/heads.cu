@@ -344,23 +344,23 @@ colsum_partial_kernel(const T* __restrict__ x, int ld, long long rows, int K, fl
         partial[(long long)blockIdx.x * K + col] = t;
     }
 }
-// block = 32 columns x 8 partial groups; fixed order within a group, fixed order over the groups
-__global__ void __launch_bounds__(256)
+// block = 32 columns x 32 partial groups; fixed order within a group, fixed order over the groups
+__global__ void __launch_bounds__(1024)
 colsum_final_kernel(const float* __restrict__ partial, int G, int K, float* __restrict__ out) {
-    __shared__ float red[8][32];
+    __shared__ float red[32][33];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + lane;
     float t = 0.f;
     if (col < K) {
-#pragma unroll 8
-        for (int g = grp; g < G; g += 8) t += __ldg(partial + (long long)g * K + col);
+#pragma unroll 4
+        for (int g = grp; g < G; g += 32) t += __ldg(partial + (long long)g * K + col);
     }
     red[grp][lane] = t;
     __syncthreads();
     if (grp == 0 && col < K) {
         float v = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v += red[q][lane];
+        for (int q = 0; q < 32; ++q) v += red[q][lane];
         out[col] = v;
     }
 }
@@ -632,7 +632,7 @@ extern "C" int fs_colsum(int device, fs_stream_t stream_, const void* x, int dty
     if (dtype == FS_BF16) colsum_partial_kernel<__nv_bfloat16, 8><<<G, 256, smem, stream>>>((const __nv_bfloat16*)x, ld, rows, K, partial_ws);
     else colsum_partial_kernel<float, 4><<<G, 256, smem, stream>>>((const float*)x, ld, rows, K, partial_ws);
     FS_RETURN_IF_LAUNCH_FAILED();
-    colsum_final_kernel<<<(K + 31) / 32, 256, 0, stream>>>(partial_ws, G, K, out);
+    colsum_final_kernel<<<(K + 31) / 32, 1024, 0, stream>>>(partial_ws, G, K, out);
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
 }

@@ -10,3 +10,6 @@ ncu --set full --clock-control none --import-source on -k regex:'edge2_fwd|edge2
 python tools/run_gather.py > gpurun_out/plain_gather.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:edgeconv_gather_smem -s 1 -c 1 -o gpurun_out/r02_gather -f python tools/run_gather.py > gpurun_out/ncu_gather.log 2>&1
 ls -la gpurun_out/*.ncu-rep gpurun_out/r02_bench_launches.csv
+python tools/torch_trace.py 1 > gpurun_out/plain_heads.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'pool_gemm|pool_lin|colsum|pool_stats' -c 8 -o gpurun_out/r02_heads -f python tools/torch_trace.py 1 > gpurun_out/ncu_heads.log 2>&1
+ls -la gpurun_out/r02_heads.ncu-rep
