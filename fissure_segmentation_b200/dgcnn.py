@@ -122,7 +122,7 @@ class ConvBlock(nn.Module):
 
     def forward_pm(self, x):
         """x (rows, C_in) -> (rows, C_out): 1x1 conv as a GEMM, then BatchNorm + LeakyReLU."""
-        y = x @ self.weight_matrix().to(x.dtype).t()
+        y = ops.linear_pm(x, self.weight_matrix())
         if self.conv.bias is not None:
             y = y + self.conv.bias.to(y.dtype)
         return self.norm_act_pm(y)
@@ -381,9 +381,9 @@ class DGCNNSeg(DGCNNBase):
             # segmentation[0] on [feats | broadcast global]: split the weight instead of materialising
             # the 1216-wide concat (models/dgcnn.py:159): local GEMM + one per-cloud bias row
             seg0 = self.segmentation[0]
-            w0 = seg0.weight_matrix().to(cdt)
-            local = feats @ w0[:, :feats.shape[1]].t()
-            per_cloud = glob @ w0[:, feats.shape[1]:].t()                        # (B, 256)
+            w0 = seg0.weight_matrix()
+            local = ops.linear_pm(feats, w0[:, :feats.shape[1]])
+            per_cloud = glob @ w0[:, feats.shape[1]:].to(cdt).t()                # (B, 256)
             h = seg0.norm_act_pm(local, rowbias=per_cloud, rows_per_cloud=N)
             h = self.segmentation[1].forward_pm(h)
             h = self.segmentation[2].forward_pm(h)

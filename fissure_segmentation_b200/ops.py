@@ -569,6 +569,16 @@ USE_POOL_GRAM = os.environ.get("FS_POOL_GRAM", "1") != "0"
 
 def _gram_f32(x):
     """X^T X with fp32 accumulation AND fp32 output (a bf16 output would lose the covariance to rounding)."""
+    P = x.shape[0]
+    S = 1
+    while S < 32 and P % (2 * S) == 0 and P // (2 * S) >= 1024:
+        S *= 2
+    if S > 1 and x.is_contiguous():
+        # rows-long reduction, tiny output: batched over row chunks (fp32 partials), then summed - the library's own
+        # split-K of the single GEMM runs at a fraction of the rate
+        xv = x.view(S, P // S, -1)
+        part = torch.bmm(xv.transpose(1, 2), xv) if x.dtype == torch.float32 else torch.bmm(xv.transpose(1, 2), xv, out_dtype=torch.float32)
+        return part.sum(dim=0)
     if x.dtype == torch.float32:
         return x.t() @ x
     return torch.mm(x.t(), x, out_dtype=torch.float32)
@@ -779,6 +789,46 @@ class _TableGemmFn(torch.autograd.Function):
                 else:
                     gw = g.t() @ x
         return gx, gw, None
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = X W^T for a tall X (rows ~ 1e5) and a small fp32 parameter W (C_out x C_in), computed in X's dtype (1x1 conv of
+    the dense heads, models/dgcnn.py:127-137). The weight gradient dW = dY^T X has a rows-long reduction and a tiny
+    output; as one GEMM the library runs it split-K at ~15 % of the tensor peak, so it is issued as a batched GEMM over
+    row chunks with fp32 partial outputs followed by a sum over the chunks. dW comes out in fp32 (the parameter's dtype):
+    no bf16 round trip and no cast kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        wc = w.detach().to(x.dtype)
+        ctx.save_for_backward(x, wc)
+        ctx.w_dtype = w.dtype
+        return x @ wc.t()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wc = ctx.saved_tensors
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = g @ wc
+        if ctx.needs_input_grad[1]:
+            P = x.shape[0]
+            S = 1
+            while S < 16 and P % (2 * S) == 0 and P // (2 * S) >= 1024:
+                S *= 2
+            if S > 1 and g.is_contiguous() and x.is_contiguous() and g.is_cuda and g.shape[1] * x.shape[1] >= 16384:
+                gt, xv = g.view(S, P // S, -1).transpose(1, 2), x.view(S, P // S, -1)
+                part = torch.bmm(gt, xv) if g.dtype == torch.float32 else torch.bmm(gt, xv, out_dtype=torch.float32)
+                gw = part.sum(dim=0)
+            else:
+                gw = (g.float().t() @ x.float())
+            gw = gw.to(ctx.w_dtype)
+        return gx, gw
+
+
+def linear_pm(x, w):
+    """x (rows, C_in) @ w (C_out, C_in)^T with w an fp32 parameter (or a view of one); see _LinearFn."""
+    return _LinearFn.apply(x, w)
 
 
 def table_gemm(x, w, tf32=False):
