@@ -49,13 +49,32 @@ def test_same_seed_gives_the_reference_parameters(gold, tag):
     assert abs(float(MF.inputs(cfg).double().abs().sum()) - g["x_checksum"]) <= 1e-9 * g["x_checksum"]
 
 
+# Per-fixture bounds = a small multiple of the deviations measured on B200 (tools/secondary_models_report.py, fp32, TF32 off):
+#   fixture               |out - ref|  |eval - ref|  worst grad-norm dev  min cosine  running stats (rel)
+#   reg_static             2.1e-5       3.3e-7        5.0e-4               1.000000    2.3e-4
+#   seg_st_imf_static      2.1e-5       3.0e-7        (zero-gradient bias) 0.999998    1.3e-3
+#   opensrc_static         8.2e-6       3.0e-8        6.4e-5               1.000000    1.0e-4
+#   cls_encoder_static     1.2e-5       3.0e-7        3.6e-7               1.000000    1.1e-5
+#   cls_encoder_dynamic    1.3e-5       5.5e-7        3.4e-7               1.000000    1.8e-5
+# No arg-max flip shows up on any of them (a flip moves single gradient entries by ~1e-3 and the cosine below 0.9999).
+TOL = {
+    "reg_static": dict(out=1e-4, ev=1e-5, gn=2e-3, cos=0.9999, run=1e-3),
+    "seg_st_imf_static": dict(out=1e-4, ev=1e-5, gn=2e-3, cos=0.9999, run=4e-3),
+    "opensrc_static": dict(out=5e-5, ev=1e-5, gn=5e-4, cos=0.9999, run=5e-4),
+    "cls_encoder_static": dict(out=1e-4, ev=1e-5, gn=1e-4, cos=0.99999, run=1e-4),
+    "cls_encoder_dynamic": dict(out=1e-4, ev=1e-5, gn=1e-4, cos=0.99999, run=1e-4),
+}
+DEFAULT_TOL = dict(out=1e-3, ev=1e-3, gn=2e-2, cos=0.999, run=1e-3)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", list(MF.CONFIGS))
 def test_forward_backward_match_the_reference(gold, tag):
-    """fp32, TF32 off. Outputs rtol/atol 1e-3 (the 1024-wide heads amplify the 1e-5 layer-wise deviations), eval
-    outputs likewise; gradients: every parameter-gradient norm within 2e-2 relative (+ a noise floor) and cosine >= 0.999 on the
-    stored small gradients (arg-max routing is discontinuous: a flipped near-tie moves single entries, see
-    DESIGN.md section 3); BatchNorm running statistics rtol 1e-3."""
+    """fp32, TF32 off, against fixtures produced by the unmodified reference. Outputs, eval outputs, every
+    parameter-gradient norm (+ a noise floor), the cosine of the stored small gradients and the BatchNorm running statistics
+    within the per-fixture bounds of TOL (arg-max routing is discontinuous: a flipped near-tie would move single gradient
+    entries, DESIGN.md section 3 - none occurs on these fixtures)."""
+    tol = TOL.get(tag, DEFAULT_TOL)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     cfg, g = MF.CONFIGS[tag], gold[tag]
@@ -67,11 +86,11 @@ def test_forward_backward_match_the_reference(gold, tag):
     with torch.no_grad():
         out_eval = m(x).cpu()
     assert out_eval.shape == g["out_eval"].shape
-    assert torch.allclose(out_eval, g["out_eval"], rtol=1e-3, atol=1e-3), float((out_eval - g["out_eval"]).abs().max())
+    assert torch.allclose(out_eval, g["out_eval"], rtol=tol["ev"], atol=tol["ev"]), float((out_eval - g["out_eval"]).abs().max())
     m.train()
     out = m(x)
     (out * MF.cotangent(out.shape, cfg["seed"]).to(DEV)).sum().backward()
-    assert torch.allclose(out.detach().cpu(), g["out"], rtol=1e-3, atol=1e-3), float((out.detach().cpu() - g["out"]).abs().max())
+    assert torch.allclose(out.detach().cpu(), g["out"], rtol=tol["out"], atol=tol["out"]), float((out.detach().cpu() - g["out"]).abs().max())
     grads = {n: p.grad.detach().cpu() for n, p in m.named_parameters() if p.grad is not None}
     assert set(grads) == set(g["grad_norms"])
     # A Linear / Conv bias in front of a BatchNorm has an exactly zero gradient; what the reference stores for it is
@@ -81,13 +100,13 @@ def test_forward_backward_match_the_reference(gold, tag):
     bad = {}
     for n, r in g["grad_norms"].items():
         mine = float(grads[n].double().norm())
-        if abs(mine - r) > 2e-2 * r + floor:
+        if abs(mine - r) > tol["gn"] * r + floor:
             bad[n] = (mine, r)
     assert not bad, bad
     for n, ref in g["grads"].items():
         if float(ref.norm()) > 10 * floor:
             cos = float(torch.nn.functional.cosine_similarity(grads[n].flatten().double(), ref.flatten().double(), dim=0))
-            assert cos >= 0.999, (n, cos, rel_err(grads[n], ref))
+            assert cos >= tol["cos"], (n, cos, rel_err(grads[n], ref))
     sd = m.state_dict()
     for n, ref in g["running"].items():
-        assert torch.allclose(sd[n].cpu(), ref, rtol=1e-3, atol=1e-5), n
+        assert torch.allclose(sd[n].cpu(), ref, rtol=tol["run"], atol=1e-5), n
