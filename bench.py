@@ -390,7 +390,7 @@ def run_train(args):
     model.precision = args.precision
     model.train()
     # the tail bucket = the EdgeConv gradients (3 % of the parameters): its all-reduce is the exposed one
-    dp = FlatDataParallel(model, n_buckets=2, tail_share=0.04)
+    dp = FlatDataParallel(model, n_buckets=2, tail_share=0.04, fused_tail=os.environ.get("FS_FUSED_TAIL", "1") != "0")
     opt = FlatAdam(dp, lr=1e-3, weight_decay=1e-5)
 
     # synthetic lung-keypoint clouds: 4 distinct batches per rank, pinned on the host

@@ -246,6 +246,40 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Tail bucket of the data-parallel step: all-reduce and Adam in ONE kernel over peer memory. Every rank reads the same
+// slice of all ranks' gradient buffers (symmetric allocations mapped over NVLink / NVSwitch; peers[r] = base pointer of
+// rank r) in the same order r = 0..world-1, so all ranks form the bit-identical sum and apply the bit-identical update;
+// nothing is written to a peer. The caller brackets the launch with device-side barriers over the same symmetric
+// allocation (the peers' gradients are complete before, and no peer starts overwriting its gradients before every rank
+// has read them).
+__global__ void adam_peers_kernel(float* __restrict__ p, const unsigned long long* __restrict__ peers, int world,
+                                  long long offset, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                  float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
+                                  const float* __restrict__ dyn, float* __restrict__ g_out) {
+    if (dyn) {
+        const float st = __ldg(dyn);
+        lr = __ldg(dyn + 1);
+        bc1 = 1.f - powf(b1, st);
+        bc2_sqrt = sqrtf(1.f - powf(b2, st));
+    }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        float gs = 0.f;
+        for (int r = 0; r < world; ++r) {
+            const float* gr = reinterpret_cast<const float*>(peers[r]) + offset;
+            gs += __ldcv(gr + e);                                   // peer memory: never from a stale cache line
+        }
+        if (g_out) g_out[e] = gs;
+        const float pv = p[e];
+        const float gv = fmaf(wd, pv, gs * gscale);
+        const float mv = fmaf(1.f - b1, gv - m[e], m[e]);
+        const float vv = fmaf(b2, v[e], (1.f - b2) * gv * gv);
+        m[e] = mv;
+        v[e] = vv;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p[e] = pv - (lr / bc1) * (mv / denom);
+    }
+}
+
 // 30-bit Morton (Z-order) code of the first three channels, 10 bits per axis over the fixed box [-2, 2)^3
 // (grid coordinates live in [-1, 1] before augmentation, augmentations.py:52-75).
 __device__ __forceinline__ uint32_t spread10(uint32_t v) {
@@ -401,6 +435,23 @@ extern "C" int fs_adam_step(int device, fs_stream_t stream_, float* param, const
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
     adam_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream_>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                weight_decay, bc1, bc2_sqrt, grad_scale, dyn_step_lr);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_adam_step_peers(int device, fs_stream_t stream_, float* param, const unsigned long long* peer_grad_ptrs,
+                                  int world, long long elem_offset, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                                  const float* dyn_step_lr, float* grad_sum_out) {
+    if (!param || !peer_grad_ptrs || !exp_avg || !exp_avg_sq || n < 0 || world < 1 || world > 64 || elem_offset < 0)
+        return FS_ERR_BAD_ARG;
+    if (n == 0) return FS_OK;
+    FS_ENTER(device);
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    adam_peers_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream_>>>(param, peer_grad_ptrs, world, elem_offset, exp_avg,
+                                                                     exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                                     bc1, bc2_sqrt, grad_scale, dyn_step_lr, grad_sum_out);
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
 }

@@ -16,7 +16,7 @@ from . import _lib
 
 
 class FlatDataParallel:
-    def __init__(self, module, n_buckets=2, process_group=None, broadcast=True, tail_share=None):
+    def __init__(self, module, n_buckets=2, process_group=None, broadcast=True, tail_share=None, fused_tail=False):
         self.module = module
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -28,7 +28,24 @@ class FlatDataParallel:
         order = list(reversed(params))
         total = sum(p.numel() for p in order)
         self.flat_param = torch.empty(total, dtype=dt, device=dev)
-        self.flat_grad = torch.zeros(total, dtype=dt, device=dev)
+        # fused_tail: the gradient buffer lives in symmetric memory (every rank maps every rank's buffer over NVLink), so
+        # the LAST bucket needs no collective call: FlatAdam reads the peers' slices directly and reduces + updates in one
+        # kernel (fs_adam_step_peers). The gradients of that bucket's parameters then stay rank-local in `.grad`.
+        self.symm = None
+        self.flat_grad = None
+        if fused_tail and self.world > 1 and dev.type == "cuda" and dt == torch.float32 and n_buckets > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(total, dtype=dt, device=dev)
+                self.symm = symm_mem.rendezvous(buf, process_group if process_group is not None else dist.group.WORLD)
+                buf.zero_()
+                self.flat_grad = buf
+            except Exception as exc:      # no peer access / symmetric memory on this system: the NCCL path below
+                import warnings
+                warnings.warn("FlatDataParallel: symmetric memory unavailable (%s); tail bucket uses all_reduce" % (exc,))
+                self.symm = None
+        if self.flat_grad is None:
+            self.flat_grad = torch.zeros(total, dtype=dt, device=dev)
         self._slices = []
         self._grad_views = []
         off = 0
@@ -105,7 +122,7 @@ class FlatDataParallel:
             if self.params[i].grad is not None:
                 self.params[i].grad = self._grad_views[i]          # .grad shows the (to be) reduced gradient
         self._sent[b] = True
-        if self.world > 1:
+        if self.world > 1 and not (self.symm is not None and b == len(self.buckets) - 1):
             self._works.append(dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.SUM, group=self.group,
                                                async_op=True))
 
@@ -157,6 +174,7 @@ class FlatAdam:
         self.exp_avg_sq = torch.zeros_like(dp.flat_param)
         self.dyn = torch.tensor([0.0, lr], dtype=torch.float32, device=dp.flat_param.device)   # [step, lr]
         self._inc = torch.tensor([1.0, 0.0], dtype=torch.float32, device=dp.flat_param.device)
+        self.tail_sum = None       # optional fp32 buffer (length of the tail bucket) that receives the peer-reduced gradient
 
     def set_lr(self, lr):
         self.lr = lr
@@ -164,6 +182,18 @@ class FlatAdam:
 
     def step(self):
         self.dyn.add_(self._inc)
-        _lib.call("fs_adam_step", self.dp.flat_param, self.dp.flat_param, self.dp.flat_grad, self.exp_avg,
-                  self.exp_avg_sq, self.dp.flat_param.numel(), float(self.lr), float(self.betas[0]),
-                  float(self.betas[1]), float(self.eps), float(self.weight_decay), 0, 1.0 / self.dp.world, self.dyn)
+        dp = self.dp
+        hyper = (float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay))
+        if dp.symm is None:
+            _lib.call("fs_adam_step", dp.flat_param, dp.flat_param, dp.flat_grad, self.exp_avg, self.exp_avg_sq,
+                      dp.flat_param.numel(), *hyper, 0, 1.0 / dp.world, self.dyn)
+            return
+        # head buckets: reduced by NCCL during backward; tail bucket: reduced from peer memory inside the update kernel
+        s, e, _ = dp.buckets[-1]
+        if s > 0:
+            _lib.call("fs_adam_step", dp.flat_param, dp.flat_param, dp.flat_grad, self.exp_avg, self.exp_avg_sq, s,
+                      *hyper, 0, 1.0 / dp.world, self.dyn)
+        dp.symm.barrier(channel=0)          # every rank's tail gradients are in its buffer
+        _lib.call("fs_adam_step_peers", dp.flat_param, dp.flat_param[s:e], dp.symm.buffer_ptrs_dev, dp.world, s,
+                  self.exp_avg[s:e], self.exp_avg_sq[s:e], e - s, *hyper, 0, 1.0 / dp.world, self.dyn, self.tail_sum)
+        dp.symm.barrier(channel=1)          # no rank overwrites its gradients before every rank has read them

@@ -441,6 +441,18 @@ int fs_adam_step(int device, fs_stream_t stream, float* param, const float* grad
                  float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int step, float grad_scale, const float* dyn_step_lr);
 
+/*
+ * Data-parallel tail: all-reduce (sum over ranks) + Adam in one kernel over PEER memory. peer_grad_ptrs is a DEVICE array
+ * of `world` base pointers of the ranks' symmetric gradient buffers (mapped into this process, e.g.
+ * torch.distributed._symmetric_memory: handle.buffer_ptrs_dev); elements [elem_offset, elem_offset + n) of every buffer are
+ * summed in rank order (bit-identical on all ranks) and applied to param / exp_avg / exp_avg_sq (local, length n).
+ * grad_sum_out (nullable, local, length n) receives the sum. The caller provides the barriers around the launch.
+ */
+int fs_adam_step_peers(int device, fs_stream_t stream, float* param, const unsigned long long* peer_grad_ptrs, int world,
+                       long long elem_offset, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, float grad_scale,
+                       const float* dyn_step_lr, float* grad_sum_out);
+
 /* ---------------------------------------------------------------- fused two-layer EdgeConv --- */
 
 /*
