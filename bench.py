@@ -390,7 +390,12 @@ def run_train(args):
     model.precision = args.precision
     model.train()
     # the tail bucket = the EdgeConv gradients (3 % of the parameters): its all-reduce is the exposed one
-    dp = FlatDataParallel(model, n_buckets=2, tail_share=0.04, fused_tail=os.environ.get("FS_FUSED_TAIL", "1") != "0")
+    # FS_FUSED_TAIL: all (default: every gradient reduced from peer memory inside the Adam kernel, no NCCL call in the
+    # step) | 1 (EdgeConv bucket from peer memory, head bucket by NCCL during backward) | 0 (NCCL only)
+    ft = os.environ.get("FS_FUSED_TAIL", "all")
+    dp = FlatDataParallel(model, n_buckets=int(os.environ.get("FS_DDP_BUCKETS", "2")), tail_share=0.04,
+                          fused_tail="all" if ft == "all" else ft != "0")
+    dp.skip_collectives = os.environ.get("FS_DDP_SKIP_COLLECTIVES", "0") == "1"      # diagnosis only
     opt = FlatAdam(dp, lr=1e-3, weight_decay=1e-5)
 
     # synthetic lung-keypoint clouds: 4 distinct batches per rank, pinned on the host

@@ -262,12 +262,7 @@ __global__ void adam_peers_kernel(float* __restrict__ p, const unsigned long lon
         bc1 = 1.f - powf(b1, st);
         bc2_sqrt = sqrtf(1.f - powf(b2, st));
     }
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        float gs = 0.f;
-        for (int r = 0; r < world; ++r) {
-            const float* gr = reinterpret_cast<const float*>(peers[r]) + offset;
-            gs += __ldcv(gr + e);                                   // peer memory: never from a stale cache line
-        }
+    auto update = [&](long long e, float gs) {
         if (g_out) g_out[e] = gs;
         const float pv = p[e];
         const float gv = fmaf(wd, pv, gs * gscale);
@@ -277,6 +272,23 @@ __global__ void adam_peers_kernel(float* __restrict__ p, const unsigned long lon
         v[e] = vv;
         const float denom = sqrtf(vv) / bc2_sqrt + eps;
         p[e] = pv - (lr / bc1) * (mv / denom);
+    };
+    // 16-byte peer loads (all ranks' loads of a quad are in flight before the first add) when the slice is aligned
+    const bool vec = (offset & 3) == 0;                    // the symmetric buffers themselves are at least 16-byte aligned
+    const long long nq = vec ? n >> 2 : 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+        float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int r = 0; r < world; ++r) {
+            const float4 t = __ldcv(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(peers[r]) + offset) + q);
+            gs.x += t.x; gs.y += t.y; gs.z += t.z; gs.w += t.w;   // rank order: identical on every rank
+        }
+        update(4 * q, gs.x); update(4 * q + 1, gs.y); update(4 * q + 2, gs.z); update(4 * q + 3, gs.w);
+    }
+    for (long long e = 4 * nq + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        float gs = 0.f;
+        for (int r = 0; r < world; ++r) gs += __ldcv(reinterpret_cast<const float*>(peers[r]) + offset + e);
+        update(e, gs);
     }
 }
 

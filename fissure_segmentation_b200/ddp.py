@@ -31,9 +31,12 @@ class FlatDataParallel:
         # fused_tail: the gradient buffer lives in symmetric memory (every rank maps every rank's buffer over NVLink), so
         # the LAST bucket needs no collective call: FlatAdam reads the peers' slices directly and reduces + updates in one
         # kernel (fs_adam_step_peers). The gradients of that bucket's parameters then stay rank-local in `.grad`.
+        # fused_tail="all" makes the whole parameter set that bucket (2.5 MB for DGCNNSeg: a one-shot read of all peers).
         self.symm = None
         self.flat_grad = None
-        if fused_tail and self.world > 1 and dev.type == "cuda" and dt == torch.float32 and n_buckets > 1:
+        if fused_tail == "all":       # every gradient through peer memory: one bucket, no collective call in the step
+            n_buckets = 1
+        if fused_tail and self.world > 1 and dev.type == "cuda" and dt == torch.float32:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 buf = symm_mem.empty(total, dtype=dt, device=dev)
@@ -85,6 +88,7 @@ class FlatDataParallel:
         self._sent = [False] * len(self.buckets)
         self._works = []
         self._reduced = False      # True between finish_backward() and zero_grad(): .grad holds all-reduced sums
+        self.skip_collectives = False   # measurement only: leaves the gradients un-reduced (what do the collectives cost?)
         if self.world > 1 and broadcast:
             dist.broadcast(self.flat_param, src=0, group=self.group)
         # Gradients are NOT accumulated into the flat buffer by autograd (that costs one add kernel per parameter
@@ -122,7 +126,7 @@ class FlatDataParallel:
             if self.params[i].grad is not None:
                 self.params[i].grad = self._grad_views[i]          # .grad shows the (to be) reduced gradient
         self._sent[b] = True
-        if self.world > 1 and not (self.symm is not None and b == len(self.buckets) - 1):
+        if self.world > 1 and not (self.symm is not None and b == len(self.buckets) - 1) and not self.skip_collectives:
             self._works.append(dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.SUM, group=self.group,
                                                async_op=True))
 

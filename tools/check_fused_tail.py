@@ -14,7 +14,8 @@ dev = torch.device("cuda", local)
 world = dist.get_world_size()
 torch.manual_seed(0)
 m = fs.DGCNNSeg(k=20, in_features=3, num_classes=4).to(dev); m.precision = "bf16"; m.train()
-dp = FlatDataParallel(m, n_buckets=2, tail_share=0.04, fused_tail=True)
+MODE = os.environ.get("FUSED", "1")          # 1: EdgeConv bucket from peer memory; all: every gradient
+dp = FlatDataParallel(m, n_buckets=2, tail_share=0.04, fused_tail="all" if MODE == "all" else True)
 assert dp.symm is not None, "symmetric memory not available"
 opt = FlatAdam(dp, lr=1e-3, weight_decay=1e-5)
 s, e, _ = dp.buckets[-1]
@@ -44,4 +45,4 @@ others = [torch.empty_like(dp.flat_param) for _ in range(world)]
 dist.all_gather(others, dp.flat_param)
 assert all(torch.equal(o, others[0]) for o in others), "ranks diverged"
 dist.barrier(); dist.destroy_process_group()
-if rank == 0: print("fused tail ok: ranks hold identical parameters")
+if rank == 0: print("fused tail (%s) ok: ranks hold identical parameters; tail = %d of %d parameters" % (MODE, e - s, dp.flat_param.numel()))
