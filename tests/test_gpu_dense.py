@@ -161,3 +161,44 @@ def test_cat_cast_matches_torch(lib, dtype):
     for t in xs:
         assert torch.equal(t.grad, g[:, off:off + t.shape[1]].float())
         off += t.shape[1]
+
+
+def test_pool_gemm_ties_and_non_finite_rows(lib, monkeypatch):
+    """tcgen05 pooled forward on awkward inputs, eval mode (running statistics): identical rows (every channel ties over all
+    points -> the lowest row must win, like a sequential arg-max), NaN / Inf rows (a NaN never wins; +Inf wins), a cloud
+    length that is not a multiple of the 128-point tile. Compared with the library-GEMM + reduction path on the same
+    bf16 operands: same arg-max rows, outputs equal up to the bf16 rounding of the materialised product."""
+    from fissure_segmentation_b200 import _lib
+    B, N, K, C = 3, 300, 192, 256
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(B * N, K, generator=gen)
+    x[:N] = x[0]                                           # cloud 0: all rows identical
+    x[N + 17] = float("nan")                               # cloud 1: one NaN row, one +Inf entry elsewhere
+    x[N + 40, 5] = float("inf")
+    x = x.to(DEV).bfloat16()
+    w = (torch.randn(C, K, generator=gen) / K ** 0.5).to(DEV)
+    w[:, 5] = w[:, 5].abs() + 0.1                          # +Inf * positive weight = +Inf for every channel
+    outs = []
+    for fused in (True, False):
+        monkeypatch.setattr(ops, "USE_POOL_GEMM", fused)
+        bn = _bn(C, 5).to(DEV)
+        with torch.no_grad():
+            bn.weight.abs_()                               # gamma >= 0: max pooling on every channel
+        bn.eval()
+        with torch.no_grad():
+            outs.append(ops.pool_linear_bn_act(x, w, bn, 0.2, B, N).float())
+    a, b = outs
+    assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.isinf(a), torch.isinf(b))
+    fin = torch.isfinite(a)
+    assert torch.isinf(a[1]).all() and (a[1] > 0).all()    # the +Inf row wins every channel of cloud 1, the NaN row none
+    assert torch.allclose(a[fin], b[fin], rtol=2e-2, atol=2e-2)
+    # the tie: arg-max of cloud 0 is row 0 for every channel
+    wc = w.to(torch.bfloat16).contiguous()
+    packed = torch.zeros(B * C, dtype=torch.int64, device=DEV)
+    _lib.call("fs_pool_gemm", x, x, x.stride(0), wc, B, N, C, K, packed)
+    sel = torch.empty(B, C, device=DEV)
+    arg = torch.empty(B, C, dtype=torch.int32, device=DEV)
+    _lib.call("fs_pool_decode", x, packed, torch.ones(C, device=DEV), B, C, sel, arg)
+    assert int(arg[0].max()) == 0 and int(arg[0].min()) == 0
+    assert (arg[1] == 40).all()
+    assert int(arg[2].min()) >= 0 and int(arg[2].max()) < N
