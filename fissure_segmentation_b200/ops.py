@@ -820,8 +820,10 @@ class _LinearFn(torch.autograd.Function):
                 gt, xv = g.view(S, P // S, -1).transpose(1, 2), x.view(S, P // S, -1)
                 part = torch.bmm(gt, xv) if g.dtype == torch.float32 else torch.bmm(gt, xv, out_dtype=torch.float32)
                 gw = part.sum(dim=0)
+            elif g.dtype == torch.float32 or not g.is_cuda:
+                gw = g.float().t() @ x.float()
             else:
-                gw = (g.float().t() @ x.float())
+                gw = torch.mm(g.t(), x, out_dtype=torch.float32)      # small output: one GEMM, fp32 result, no casts of X
             gw = gw.to(ctx.w_dtype)
         return gx, gw
 
