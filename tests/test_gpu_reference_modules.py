@@ -95,3 +95,36 @@ def test_b200_module_against_the_reference_module_on_the_same_gpu(lib, dynamic):
                 assert_close(a, b, 1e-4, 1e-5, n)
     else:
         assert float((diff > 1e-4 + 1e-4 * lr.abs()).float().mean()) < 0.05
+
+
+def test_linear1_forward_hook_sees_the_reference_global_feature(lib):
+    """models/dg_ssm.py:41 (MultiHeadDGCNN) hangs extra regression heads on the INPUT of `linear1`, captured with a
+    forward hook. Same hook on the reference dgcnn_opensrc.DGCNN and on the B200 twin, same weights and input: the
+    captured (B, 2*emb_dims) global feature and the main output agree, and a loss on the captured feature back-propagates
+    into the EdgeConv weights of the twin."""
+    from types import SimpleNamespace
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    _, ref_opensrc, _ = reference_shim.load()
+    from fissure_segmentation_b200.dgcnn_opensrc import DGCNN
+    args = SimpleNamespace(k=20, emb_dims=256, dropout=0.0, static=True)
+    torch.manual_seed(5)
+    ref = ref_opensrc.DGCNN(args, 3, 10).to(DEV).eval()
+    ours = DGCNN(args, 3, 10).to(DEV).eval()
+    ours.load_state_dict(ref.state_dict())
+    ours.precision = "fp32"
+    seen = {}
+    ref.linear1.register_forward_hook(lambda m, inp, out: seen.__setitem__("ref", inp[0]))
+    ours.linear1.register_forward_hook(lambda m, inp, out: seen.__setitem__("ours", inp[0]))
+    x, _ = synth.make_batch(3, 1024, seed=21, jitter=True)
+    x = x.to(DEV)
+    with torch.no_grad():
+        out_ref = ref(x)
+    out = ours(x)
+    assert seen["ours"].shape == seen["ref"].shape == (3, 2 * args.emb_dims)
+    assert_close(seen["ours"], seen["ref"], 1e-4, 1e-4, "hooked global feature")
+    assert_close(out, out_ref, 1e-4, 1e-4, "main head")
+    ours.zero_grad()
+    seen["ours"].square().mean().backward()
+    g = ours.conv1[0].weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
