@@ -113,13 +113,22 @@ colstats_kernel(const T* __restrict__ x, int ld, long long rows, int C, const fl
 template <typename T, typename OT>
 __global__ void __launch_bounds__(DN_THREADS)
 bn_act_apply_kernel(const T* __restrict__ x, int ld, long long rows, int C, const float* __restrict__ bias, int N,
-                    const float* __restrict__ coef, float slope, OT* __restrict__ out, int ld_out) {
+                    const float* __restrict__ coef, const FsBnFin fin, float slope, OT* __restrict__ out, int ld_out) {
     constexpr int V = Vec<T>::N;
     RowMap m(C, V);
     for (int cc = m.c0; cc < C; cc += m.tpr * V) {
         float mu[V], sc[V], be[V];
+        if (fin.stats) {        // coefficients straight from the statistics; block 0, first row group publishes them
+            const bool publish = blockIdx.x == 0 && m.r == 0;
 #pragma unroll
-        for (int i = 0; i < V; ++i) { mu[i] = __ldg(coef + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i); be[i] = __ldg(coef + 3 * C + cc + i); }
+            for (int i = 0; i < V; ++i) {
+                float inv;
+                fs_bn_fin_channel(fin, cc + i, C, publish, mu[i], inv, sc[i], be[i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) { mu[i] = __ldg(coef + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i); be[i] = __ldg(coef + 3 * C + cc + i); }
+        }
         for (long long row = (long long)blockIdx.x * m.rows_per_pass + m.r; row < rows; row += (long long)gridDim.x * m.rows_per_pass) {
             float f[V];
             Vec<T>::load(x + row * ld + cc, f);
@@ -435,16 +444,16 @@ extern "C" int fs_colstats(int device, fs_stream_t stream_, const void* x, int d
     return FS_OK;
 }
 
-extern "C" int fs_bn_act_apply(int device, fs_stream_t stream_, const void* x, int dtype, int ld, long long rows, int C,
-                               const float* rowbias, int N, const float* coef, float slope, void* out, int out_dtype,
-                               int ld_out) {
-    if (!x || !coef || !out || rows <= 0 || ld < C || ld_out < C || (rowbias && N <= 0)) return FS_ERR_BAD_ARG;
+static int bn_act_apply_launch(int device, fs_stream_t stream_, const void* x, int dtype, int ld, long long rows, int C,
+                               const float* rowbias, int N, const float* coef, const FsBnFin& fin, float slope, void* out,
+                               int out_dtype, int ld_out) {
+    if (!x || !out || rows <= 0 || ld < C || ld_out < C || (rowbias && N <= 0)) return FS_ERR_BAD_ARG;
     const int vec = dtype == FS_BF16 ? 8 : 4;
     if (!pow2_width(C, vec)) return FS_ERR_UNSUPPORTED;
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int grid = dn_grid(rows, rows_per_pass(C, vec));
-#define GO(T, OT) bn_act_apply_kernel<<<grid, DN_THREADS, 0, stream>>>((const T*)x, ld, rows, C, rowbias, N, coef, slope, (OT*)out, ld_out)
+#define GO(T, OT) bn_act_apply_kernel<<<grid, DN_THREADS, 0, stream>>>((const T*)x, ld, rows, C, rowbias, N, coef, fin, slope, (OT*)out, ld_out)
     if (dtype == FS_BF16 && out_dtype == FS_BF16) GO(__nv_bfloat16, __nv_bfloat16);
     else if (dtype == FS_BF16) GO(__nv_bfloat16, float);
     else if (out_dtype == FS_BF16) GO(float, __nv_bfloat16);
@@ -452,6 +461,26 @@ extern "C" int fs_bn_act_apply(int device, fs_stream_t stream_, const void* x, i
 #undef GO
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
+}
+
+extern "C" int fs_bn_act_apply(int device, fs_stream_t stream_, const void* x, int dtype, int ld, long long rows, int C,
+                               const float* rowbias, int N, const float* coef, float slope, void* out, int out_dtype,
+                               int ld_out) {
+    if (!coef) return FS_ERR_BAD_ARG;
+    FsBnFin fin{};
+    return bn_act_apply_launch(device, stream_, x, dtype, ld, rows, C, rowbias, N, coef, fin, slope, out, out_dtype, ld_out);
+}
+
+// The same with the BatchNorm finalisation (fs_bn_finalize) folded in: coefficients from `stats`, published to coef_out,
+// running statistics updated.
+extern "C" int fs_bn_act_apply_fin(int device, fs_stream_t stream_, const void* x, int dtype, int ld, long long rows, int C,
+                                   const float* rowbias, int N, const double* stats, double count, const float* gamma,
+                                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                   long long* num_batches_tracked, float* coef_out, float slope, void* out, int out_dtype,
+                                   int ld_out) {
+    if (!stats || !gamma || !beta || !coef_out || count <= 0) return FS_ERR_BAD_ARG;
+    FsBnFin fin{stats, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, coef_out};
+    return bn_act_apply_launch(device, stream_, x, dtype, ld, rows, C, rowbias, N, nullptr, fin, slope, out, out_dtype, ld_out);
 }
 
 extern "C" int fs_bn_act_bwd(int device, fs_stream_t stream_, const void* g, int g_dtype, int ldg, const void* x, int dtype,

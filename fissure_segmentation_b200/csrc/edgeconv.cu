@@ -269,7 +269,18 @@ __global__ void bn_coef_eval_kernel(int Cp, const float* __restrict__ gamma, con
 template <typename TT, typename OT>
 __global__ void __launch_bounds__(256)
 edgeconv_apply_kernel(const float* __restrict__ sel, const TT* __restrict__ table, int ld, long long P, int Cp,
-                      const float* __restrict__ coef, OT* __restrict__ out, int ld_out) {
+                      const float* __restrict__ coef, const FsBnFin fin, OT* __restrict__ out, int ld_out) {
+    extern __shared__ float ea_coef[];          // [3][Cp]: mean | scale | beta (from `coef`, or from the statistics)
+    for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+        float mu, inv, sc, be;
+        if (fin.stats) {
+            fs_bn_fin_channel(fin, c, Cp, blockIdx.x == 0, mu, inv, sc, be);
+        } else {
+            mu = __ldg(coef + c); sc = __ldg(coef + 2 * Cp + c); be = __ldg(coef + 3 * Cp + c);
+        }
+        ea_coef[c] = mu; ea_coef[Cp + c] = sc; ea_coef[2 * Cp + c] = be;
+    }
+    __syncthreads();
     const int q = Cp >> 2;
     const long long total = P * q;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -281,7 +292,7 @@ edgeconv_apply_kernel(const float* __restrict__ sel, const TT* __restrict__ tabl
         else { b[0] = b[1] = b[2] = b[3] = 0.f; }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float mu = __ldg(coef + c0 + i), sc = __ldg(coef + 2 * Cp + c0 + i), be = __ldg(coef + 3 * Cp + c0 + i);
+            const float mu = ea_coef[c0 + i], sc = ea_coef[Cp + c0 + i], be = ea_coef[2 * Cp + c0 + i];
             o[i] = fs_leaky(fmaf(sc, (s[i] + b[i]) - mu, be));
         }
         store4(out + pt * ld_out + c0, o);
@@ -811,23 +822,42 @@ extern "C" int fs_bn_coef_eval(int device, fs_stream_t stream_, int Cp, const fl
     return FS_OK;
 }
 
-extern "C" int fs_edgeconv_apply(int device, fs_stream_t stream_, const float* sel, const void* table, int dtype,
-                                 int ld, long long P, int Cp, const float* coef, void* out, int out_dtype, int ld_out) {
-    if (!sel || !coef || !out || P < 0 || Cp <= 0 || Cp % 4 || (table && ld < 2 * Cp) || ld_out < Cp) return FS_ERR_BAD_ARG;
+static int edgeconv_apply_launch(int device, fs_stream_t stream_, const float* sel, const void* table, int dtype, int ld,
+                                 long long P, int Cp, const float* coef, const FsBnFin& fin, void* out, int out_dtype,
+                                 int ld_out) {
+    if (!sel || !out || P < 0 || Cp <= 0 || Cp % 4 || Cp > 2048 || (table && ld < 2 * Cp) || ld_out < Cp) return FS_ERR_BAD_ARG;
     if (P == 0) return FS_OK;
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int grid = ec_grid(P * (Cp / 4), 256);
+    const size_t smem = (size_t)3 * Cp * sizeof(float);
     if (dtype == FS_BF16 && out_dtype == FS_BF16)
-        edgeconv_apply_kernel<<<grid, 256, 0, stream>>>(sel, (const __nv_bfloat16*)table, ld, P, Cp, coef, (__nv_bfloat16*)out, ld_out);
+        edgeconv_apply_kernel<<<grid, 256, smem, stream>>>(sel, (const __nv_bfloat16*)table, ld, P, Cp, coef, fin, (__nv_bfloat16*)out, ld_out);
     else if (dtype == FS_BF16)
-        edgeconv_apply_kernel<<<grid, 256, 0, stream>>>(sel, (const __nv_bfloat16*)table, ld, P, Cp, coef, (float*)out, ld_out);
+        edgeconv_apply_kernel<<<grid, 256, smem, stream>>>(sel, (const __nv_bfloat16*)table, ld, P, Cp, coef, fin, (float*)out, ld_out);
     else if (out_dtype == FS_BF16)
-        edgeconv_apply_kernel<<<grid, 256, 0, stream>>>(sel, (const float*)table, ld, P, Cp, coef, (__nv_bfloat16*)out, ld_out);
+        edgeconv_apply_kernel<<<grid, 256, smem, stream>>>(sel, (const float*)table, ld, P, Cp, coef, fin, (__nv_bfloat16*)out, ld_out);
     else
-        edgeconv_apply_kernel<<<grid, 256, 0, stream>>>(sel, (const float*)table, ld, P, Cp, coef, (float*)out, ld_out);
+        edgeconv_apply_kernel<<<grid, 256, smem, stream>>>(sel, (const float*)table, ld, P, Cp, coef, fin, (float*)out, ld_out);
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
+}
+
+extern "C" int fs_edgeconv_apply(int device, fs_stream_t stream_, const float* sel, const void* table, int dtype,
+                                 int ld, long long P, int Cp, const float* coef, void* out, int out_dtype, int ld_out) {
+    if (!coef) return FS_ERR_BAD_ARG;
+    FsBnFin fin{};
+    return edgeconv_apply_launch(device, stream_, sel, table, dtype, ld, P, Cp, coef, fin, out, out_dtype, ld_out);
+}
+
+// The same with fs_bn_finalize folded in (coefficients from `stats`, published to coef_out, running statistics updated).
+extern "C" int fs_edgeconv_apply_fin(int device, fs_stream_t stream_, const float* sel, const void* table, int dtype, int ld,
+                                     long long P, int Cp, const double* stats, double count, const float* gamma,
+                                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                     long long* num_batches_tracked, float* coef_out, void* out, int out_dtype, int ld_out) {
+    if (!stats || !gamma || !beta || !coef_out || count <= 0) return FS_ERR_BAD_ARG;
+    FsBnFin fin{stats, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, coef_out};
+    return edgeconv_apply_launch(device, stream_, sel, table, dtype, ld, P, Cp, nullptr, fin, out, out_dtype, ld_out);
 }
 
 extern "C" int fs_reverse_graph(int device, fs_stream_t stream_, const int32_t* idx, int B, int N, int k,

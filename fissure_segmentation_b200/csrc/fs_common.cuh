@@ -122,6 +122,45 @@ __host__ __device__ inline long long fs_stats_doubles(int C) { return 3ll * C + 
 
 // Threads whose (threadIdx.x % period) agree own the same NCH channels chan[0..NCH).
 // buf: shared double[2 * NCH * blockDim.x]. Every thread of the block must call this exactly once per kernel.
+// BatchNorm finalisation folded into the kernel that applies it (saves one tiny launch per BatchNorm layer and step):
+// every block derives the coefficients of the channels it needs from the finished statistics; ONE designated thread per
+// channel also publishes them (coef = [mean | invstd | scale | beta], the layout of fs_bn_finalize) and updates the
+// running statistics / num_batches_tracked exactly like bn_finalize_kernel.
+struct FsBnFin {
+    const double* stats;        // nullptr: no inline finalisation (coefficients are read from `coef`)
+    double count;
+    const float* gamma;
+    const float* beta;
+    float eps, momentum;
+    float* running_mean;
+    float* running_var;
+    long long* nbt;
+    float* coef_out;
+};
+__device__ __forceinline__ void fs_bn_fin_channel(const FsBnFin& f, int c, int C, bool publish, float& mean_f, float& invstd,
+                                                  float& scale, float& beta) {
+    const double m1 = f.stats[c] / f.count;
+    double var = f.stats[C + c] / f.count - m1 * m1;
+    if (var < 0.0) var = 0.0;
+    const double mean = m1 + f.stats[2 * C + c];
+    invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+    mean_f = (float)mean;
+    scale = __ldg(f.gamma + c) * invstd;
+    beta = __ldg(f.beta + c);
+    if (publish) {
+        f.coef_out[c] = mean_f;
+        f.coef_out[C + c] = invstd;
+        f.coef_out[2 * C + c] = scale;
+        f.coef_out[3 * C + c] = beta;
+        if (f.running_mean) f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean_f;
+        if (f.running_var) {
+            const double unbiased = f.count > 1.0 ? var * f.count / (f.count - 1.0) : var;
+            f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+        }
+        if (c == 0 && f.nbt) *f.nbt += 1;
+    }
+}
+
 template <int NCH>
 __device__ __forceinline__ void fs_stats_commit_impl(double* buf, const double* s1, const double* s2, const int* chan,
                                                      int period, int C, double* gstats, unsigned block_linear,

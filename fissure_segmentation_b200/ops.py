@@ -270,6 +270,34 @@ def _bn_coef(table_ref, stats, count, gamma, beta, running_mean, running_var, nb
     return coef
 
 
+def _bn_then_edgeconv_apply(ref, sel, table, dt, ld, P, Cp, stats, count, gamma, beta, running_mean, running_var, nbt,
+                            training, eps, momentum, out):
+    """BatchNorm coefficients + fs_edgeconv_apply. Training: ONE launch (the finalisation of the batch statistics is
+    folded into the apply kernel, which also publishes the coefficients for the backward); eval: running statistics."""
+    if training:
+        coef = torch.empty(4 * Cp, dtype=torch.float32, device=ref.device)
+        _lib.call("fs_edgeconv_apply_fin", ref, sel, table, dt, ld, P, Cp, stats, float(count), gamma, beta, eps, momentum,
+                  running_mean, running_var, nbt, coef, out, _lib.dtype_code(out), out.stride(0))
+        return coef
+    coef = _bn_coef(ref, None, 1, gamma, beta, running_mean, running_var, nbt, False, Cp, eps, momentum)
+    _lib.call("fs_edgeconv_apply", ref, sel, table, dt, ld, P, Cp, coef, out, _lib.dtype_code(out), out.stride(0))
+    return coef
+
+
+def _bn_then_act_apply(ref, src, src_dt, ld, rows, C, rowbias, N, stats, count, gamma, beta, running_mean, running_var, nbt,
+                       training, eps, momentum, slope, out):
+    """The same for fs_bn_act_apply (dense heads, pooled values)."""
+    if training:
+        coef = torch.empty(4 * C, dtype=torch.float32, device=ref.device)
+        _lib.call("fs_bn_act_apply_fin", ref, src, src_dt, ld, rows, C, rowbias, N, stats, float(count), gamma, beta, eps,
+                  momentum, running_mean, running_var, nbt, coef, float(slope), out, _lib.dtype_code(out), out.stride(0))
+        return coef
+    coef = _bn_coef(ref, None, 1, gamma, beta, running_mean, running_var, nbt, False, C, eps, momentum)
+    _lib.call("fs_bn_act_apply", ref, src, src_dt, ld, rows, C, rowbias, N, coef, float(slope), out, _lib.dtype_code(out),
+              out.stride(0))
+    return coef
+
+
 class _EdgeConvFn(torch.autograd.Function):
     """Single-layer EdgeConv on the per-point table T = [a | b]:
     out_i = LeakyReLU(BN(max_j (a_j + b_i))), models/dgcnn.py:226-243 with a one-layer shared MLP."""
@@ -290,11 +318,9 @@ class _EdgeConvFn(torch.autograd.Function):
         rev_ptr = graph.reverse()[0] if training else None      # in-degrees for the batch statistics
         _lib.call("fs_edgeconv_gather", table, table, dt, table.stride(0), idx, B, N, k, Cp, gamma32, rev_ptr, sel, arg,
                   sy, stats)
-        coef = _bn_coef(table, stats, P * k, gamma32, beta32, running_mean, running_var, nbt, training, Cp, eps,
-                        momentum)
         out = torch.empty(P, Cp, dtype=table.dtype, device=dev)
-        _lib.call("fs_edgeconv_apply", table, sel, table, dt, table.stride(0), P, Cp, coef, out, _lib.dtype_code(out),
-                  out.stride(0))
+        coef = _bn_then_edgeconv_apply(table, sel, table, dt, table.stride(0), P, Cp, stats, P * k, gamma32, beta32,
+                                       running_mean, running_var, nbt, training, eps, momentum, out)
         ctx.graph = graph
         ctx.training = training
         ctx.save_for_backward(table, sel, arg, sy, coef)
@@ -489,10 +515,9 @@ class _BnActFn(torch.autograd.Function):
         if training:
             stats = _stats_buffer(C, x.device)
             _lib.call("fs_colstats", x, x, _lib.dtype_code(x), x.stride(0), rows, C, rb, N, stats)
-        coef = _bn_coef(x, stats, rows, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
         out = torch.empty(rows, C, dtype=x.dtype, device=x.device)
-        _lib.call("fs_bn_act_apply", x, x, _lib.dtype_code(x), x.stride(0), rows, C, rb, N, coef, float(slope), out,
-                  _lib.dtype_code(out), out.stride(0))
+        coef = _bn_then_act_apply(x, x, _lib.dtype_code(x), x.stride(0), rows, C, rb, N, stats, rows, gamma32, beta32,
+                                  running_mean, running_var, nbt, training, eps, momentum, slope, out)
         ctx.save_for_backward(x, rb, coef)
         ctx.training, ctx.slope, ctx.N = training, slope, N
         return out
@@ -536,9 +561,9 @@ class _PoolBnActFn(torch.autograd.Function):
         stats = _stats_buffer(C, dev) if training else None
         packed = _zeros64(B * C, dev).view(torch.int64)
         _lib.call("fs_pool_reduce", x, x, _lib.dtype_code(x), x.stride(0), B, N, C, gamma32, sel, arg, stats, packed)
-        coef = _bn_coef(x, stats, B * N, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
         out = torch.empty(B, C, dtype=x.dtype, device=dev)
-        _lib.call("fs_bn_act_apply", x, sel, 0, C, B, C, None, 1, coef, float(slope), out, _lib.dtype_code(out), C)
+        coef = _bn_then_act_apply(x, sel, 0, C, B, C, None, 1, stats, B * N, gamma32, beta32, running_mean, running_var, nbt,
+                                  training, eps, momentum, slope, out)
         ctx.save_for_backward(x, sel, arg, coef)
         ctx.training, ctx.slope, ctx.B, ctx.N = training, slope, B, N
         return out
@@ -635,9 +660,9 @@ class _PoolLinearFn(torch.autograd.Function):
             y = x @ wc.t()
             _lib.call("fs_pool_reduce", y, y, _lib.dtype_code(y), y.stride(0), B, N, C, gamma32, sel, arg, stats, packed)
             ref = y
-        coef = _bn_coef(ref, stats, B * N, gamma32, beta32, running_mean, running_var, nbt, training, C, eps, momentum)
         out = torch.empty(B, C, dtype=x.dtype, device=dev)
-        _lib.call("fs_bn_act_apply", x, sel, 0, C, B, C, None, 1, coef, float(slope), out, _lib.dtype_code(out), C)
+        coef = _bn_then_act_apply(ref, sel, 0, C, B, C, None, 1, stats, B * N, gamma32, beta32, running_mean, running_var,
+                                  nbt, training, eps, momentum, slope, out)
         ctx.save_for_backward(x, wc, sel, arg, coef, colsum, wg)
         ctx.training, ctx.slope, ctx.B, ctx.N, ctx.w_dtype = training, slope, B, N, w.dtype
         return out
@@ -963,9 +988,9 @@ class _EdgeConv2Fn(torch.autograd.Function):
             gh = _zeros64((C1 * C1 + C1 + 1) // 2 + 1, dev).view(torch.float32)
             gram, hsum = gh[:C1 * C1].view(C1, C1), gh[C1 * C1:C1 * C1 + C1]
         _lib.call("fs_edge2_fwd", x, x, x.stride(0), graph.idx, B, N, k, w1m, coef1, w2m, C2, g2f, sel, arg, stats, gram, hsum)
-        coef2 = _bn_coef(x, stats, P * k, g2f, b2f, rm2, rv2, nbt2, training, C2, eps, momentum)
         out = torch.empty(P, C2, dtype=torch.float32, device=dev)
-        _lib.call("fs_edgeconv_apply", x, sel, None, 0, 0, P, C2, coef2, out, _lib.dtype_code(out), out.stride(0))
+        coef2 = _bn_then_edgeconv_apply(x, sel, None, 0, 0, P, C2, stats, P * k, g2f, b2f, rm2, rv2, nbt2, training, eps,
+                                        momentum, out)
         ctx.graph, ctx.training = graph, training
         ctx.shapes = (w1.shape, w2.shape)
         ctx.save_for_backward(x, w1m, w2m, coef1, coef2, sel, arg, mom, gram, hsum)

@@ -183,6 +183,11 @@ int fs_bn_coef_eval(int device, fs_stream_t stream, int Cp, const float* gamma, 
 int fs_edgeconv_apply(int device, fs_stream_t stream, const float* sel, const void* table,
                       int dtype, int ld, long long P, int Cp, const float* coef, void* out,
                       int out_dtype, int ld_out);
+/* The same with fs_bn_finalize folded in (training): see fs_bn_act_apply_fin. */
+int fs_edgeconv_apply_fin(int device, fs_stream_t stream, const float* sel, const void* table, int dtype, int ld,
+                          long long P, int Cp, const double* stats, double count, const float* gamma,
+                          const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                          long long* num_batches_tracked, float* coef_out, void* out, int out_dtype, int ld_out);
 
 /*
  * Eval-mode single pass: gather + select + folded BN + LeakyReLU straight to `out`.
@@ -302,6 +307,13 @@ int fs_colstats(int device, fs_stream_t stream, const void* x, int dtype, int ld
 int fs_bn_act_apply(int device, fs_stream_t stream, const void* x, int dtype, int ld, long long rows,
                     int C, const float* rowbias, int N, const float* coef, float slope, void* out,
                     int out_dtype, int ld_out);
+/* fs_bn_act_apply with fs_bn_finalize folded in (training): coefficients from `stats` (fs_colstats layout), published to
+ * coef_out [4C] for the backward, running statistics / num_batches_tracked updated - one launch instead of two. */
+int fs_bn_act_apply_fin(int device, fs_stream_t stream, const void* x, int dtype, int ld, long long rows, int C,
+                        const float* rowbias, int N, const double* stats, double count, const float* gamma,
+                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                        long long* num_batches_tracked, float* coef_out, float slope, void* out, int out_dtype,
+                        int ld_out);
 int fs_bn_act_bwd(int device, fs_stream_t stream, const void* g, int g_dtype, int ldg, const void* x,
                   int dtype, int ld, long long rows, int C, const float* rowbias, int N, const float* coef,
                   float slope, double* dgb, double count, int train_stats, void* dx, int dx_dtype,
