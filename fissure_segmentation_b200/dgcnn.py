@@ -122,9 +122,7 @@ class ConvBlock(nn.Module):
 
     def forward_pm(self, x):
         """x (rows, C_in) -> (rows, C_out): 1x1 conv as a GEMM, then BatchNorm + LeakyReLU."""
-        y = ops.linear_pm(x, self.weight_matrix())
-        if self.conv.bias is not None:
-            y = y + self.conv.bias.to(y.dtype)
+        y = ops.linear_pm(x, self.weight_matrix(), self.conv.bias)       # bias added by the GEMM, its gradient by a GEMM too
         return self.norm_act_pm(y)
 
 

@@ -536,7 +536,7 @@ class _BnActFn(torch.autograd.Function):
                   ctx.N, coef, float(ctx.slope), dgb, float(rows), int(ctx.training), dx, _lib.dtype_code(dx),
                   dx.stride(0))
         dgb32 = dgb[:2 * C].float()
-        drb = dx.view(-1, ctx.N, C).sum(dim=1, dtype=torch.float32) if rb is not None else None
+        drb = _cloudsum_f32(dx, rows // ctx.N, ctx.N) if rb is not None else None
         return dx, drb, dgb32[C:], dgb32[:C], None, None, None, None, None, None, None, None
 
 
@@ -816,6 +816,35 @@ class _TableGemmFn(torch.autograd.Function):
         return gx, gw, None
 
 
+_ones_cache = {}
+
+
+def _ones(n, dtype, device):
+    key = (n, dtype, torch.device(device))
+    t = _ones_cache.get(key)
+    if t is None:
+        t = torch.ones(n, dtype=dtype, device=device)
+        _ones_cache[key] = t
+    return t
+
+
+def _rowsum_f32(g):
+    """Column sums of a tall (rows, C) table as a GEMM with a row of ones (fp32 result): ATen's reduction over the long
+    dimension of a narrow table runs at a few percent of the memory rate."""
+    if not g.is_cuda or g.dtype == torch.float32 or not g.is_contiguous():
+        return g.float().sum(dim=0)
+    return torch.mm(_ones(g.shape[0], g.dtype, g.device).unsqueeze(0), g, out_dtype=torch.float32).squeeze(0)
+
+
+def _cloudsum_f32(dx, B, N):
+    """Per-cloud column sums of a (B*N, C) table -> (B, C) fp32, as a batched GEMM with a row of ones."""
+    C = dx.shape[1]
+    if not dx.is_cuda or dx.dtype == torch.float32 or not dx.is_contiguous():
+        return dx.view(B, N, C).sum(dim=1, dtype=torch.float32)
+    ones = _ones(N, dx.dtype, dx.device).view(1, 1, N).expand(B, 1, N)
+    return torch.bmm(ones, dx.view(B, N, C), out_dtype=torch.float32).squeeze(1)
+
+
 class _LinearFn(torch.autograd.Function):
     """y = X W^T for a tall X (rows ~ 1e5) and a small fp32 parameter W (C_out x C_in), computed in X's dtype (1x1 conv of
     the dense heads, models/dgcnn.py:127-137). The weight gradient dW = dY^T X has a rows-long reduction and a tiny
@@ -824,10 +853,13 @@ class _LinearFn(torch.autograd.Function):
     no bf16 round trip and no cast kernel."""
 
     @staticmethod
-    def forward(ctx, x, w):
+    def forward(ctx, x, w, bias=None):
         wc = w.detach().to(x.dtype)
         ctx.save_for_backward(x, wc)
         ctx.w_dtype = w.dtype
+        ctx.has_bias = bias is not None
+        if bias is not None:
+            return torch.addmm(bias.detach().to(x.dtype), x, wc.t())
         return x @ wc.t()
 
     @staticmethod
@@ -850,12 +882,15 @@ class _LinearFn(torch.autograd.Function):
             else:
                 gw = torch.mm(g.t(), x, out_dtype=torch.float32)      # small output: one GEMM, fp32 result, no casts of X
             gw = gw.to(ctx.w_dtype)
-        return gx, gw
+        gb = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = _rowsum_f32(g).to(ctx.w_dtype)
+        return gx, gw, gb
 
 
-def linear_pm(x, w):
-    """x (rows, C_in) @ w (C_out, C_in)^T with w an fp32 parameter (or a view of one); see _LinearFn."""
-    return _LinearFn.apply(x, w)
+def linear_pm(x, w, bias=None):
+    """x (rows, C_in) @ w (C_out, C_in)^T (+ bias) with w, bias fp32 parameters (or views of one); see _LinearFn."""
+    return _LinearFn.apply(x, w, bias)
 
 
 def table_gemm(x, w, tf32=False):
