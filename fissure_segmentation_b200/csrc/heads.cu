@@ -365,6 +365,34 @@ colsum_final_kernel(const float* __restrict__ partial, int G, int K, float* __re
     }
 }
 
+// ---- network output: per-point logits of the (Morton-)sorted cloud, point-major (B*N, C) in the compute dtype ->
+// (B, C, N) fp32 in the CALLER's point order: out[b, c, perm[b, n]] = logits[b*N + n, c] (perm nullable = identity),
+// and the reverse for the gradient. Replaces permute + cast + scatter (and gather + permute + cast on the way back).
+template <typename T>
+__global__ void logits_out_kernel(const T* __restrict__ logits, int ld, const long long* __restrict__ perm, int B, int N, int C,
+                                  float* __restrict__ out) {
+    const long long total = (long long)B * N;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / N;
+        const long long dst = perm ? perm[e] : e - b * N;
+        const T* row = logits + e * ld;
+        float* ob = out + b * C * N + dst;
+        for (int c = 0; c < C; ++c) ob[(long long)c * N] = ld_as_float(row + c);
+    }
+}
+template <typename T>
+__global__ void logits_out_bwd_kernel(const float* __restrict__ g, const long long* __restrict__ perm, int B, int N, int C,
+                                      T* __restrict__ dlogits, int ld) {
+    const long long total = (long long)B * N;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / N;
+        const long long src = perm ? perm[e] : e - b * N;
+        const float* gb = g + b * C * N + src;
+        T* row = dlogits + e * ld;
+        for (int c = 0; c < C; ++c) st_from_float(row + c, gb[(long long)c * N]);
+    }
+}
+
 // ---- gradient bucket: up to 32 fp32 tensors copied into their slices of a flat buffer by ONE launch. The table of
 // (source, destination, element count) travels as a kernel parameter, so nothing is staged through device memory.
 struct MultiCopy {
@@ -705,5 +733,31 @@ extern "C" int fs_multi_copy_f32(int device, fs_stream_t stream_, int n, const v
         multi_copy_kernel<<<chunks, 256, 0, stream>>>(t);
         FS_RETURN_IF_LAUNCH_FAILED();
     }
+    return FS_OK;
+}
+
+extern "C" int fs_logits_out(int device, fs_stream_t stream_, const void* logits, int dtype, int ld, const long long* perm, int B,
+                             int N, int C, float* out) {
+    if (!logits || !out || B <= 0 || N <= 0 || C <= 0 || ld < C) return FS_ERR_BAD_ARG;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long total = (long long)B * N;
+    const int grid = (int)(fs_div_up(total, 256) < (long long)FS_NUM_SMS * 8 ? fs_div_up(total, 256) : (long long)FS_NUM_SMS * 8);
+    if (dtype == FS_BF16) logits_out_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)logits, ld, perm, B, N, C, out);
+    else logits_out_kernel<<<grid, 256, 0, stream>>>((const float*)logits, ld, perm, B, N, C, out);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_logits_out_bwd(int device, fs_stream_t stream_, const float* g, const long long* perm, int B, int N, int C,
+                                 void* dlogits, int dtype, int ld) {
+    if (!g || !dlogits || B <= 0 || N <= 0 || C <= 0 || ld < C) return FS_ERR_BAD_ARG;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long total = (long long)B * N;
+    const int grid = (int)(fs_div_up(total, 256) < (long long)FS_NUM_SMS * 8 ? fs_div_up(total, 256) : (long long)FS_NUM_SMS * 8);
+    if (dtype == FS_BF16) logits_out_bwd_kernel<<<grid, 256, 0, stream>>>(g, perm, B, N, C, (__nv_bfloat16*)dlogits, ld);
+    else logits_out_bwd_kernel<<<grid, 256, 0, stream>>>(g, perm, B, N, C, (float*)dlogits, ld);
+    FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
 }

@@ -7,6 +7,8 @@ libfissure_b200.so; the parameter containers are ordinary nn.Conv / nn.BatchNorm
 created in the reference's order (identical initial weights for the same seed) but whose own
 `forward` is never used on the EdgeConv path.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -284,7 +286,7 @@ class DGCNNBase(PointSegmentationModelBase):
         # Sort every cloud along the Morton curve of its coordinates before the EdgeConvs: consecutive rows are
         # then spatial neighbours and the k-row gathers of a CTA's point range overlap (L1/L2 hits). Every
         # operator is permutation-equivariant; per-point outputs are un-permuted before they are returned.
-        self.spatial_sort = True
+        self.spatial_sort = os.environ.get("FS_SPATIAL_SORT", "1") != "0"
 
         if image_feat_module:
             if in_features < 4:
@@ -386,7 +388,7 @@ class DGCNNSeg(DGCNNBase):
             h = self.segmentation[1].forward_pm(h)
             h = self.segmentation[2].forward_pm(h)
             logits = self.segmentation[3].forward_pm(h)                          # (B*N, classes)
-            return self._unsort_points(logits.view(B, N, -1).permute(0, 2, 1).float())
+            return ops.logits_out(logits, self._perm, B, N)          # (B, classes, N) fp32 in the caller's point order
 
 
 class DGCNNReg(DGCNNBase):

@@ -816,6 +816,37 @@ class _TableGemmFn(torch.autograd.Function):
         return gx, gw, None
 
 
+class _LogitsOutFn(torch.autograd.Function):
+    """(B*N, C) point-major logits of the internally sorted cloud -> (B, C, N) fp32 in the caller's order, one kernel each
+    way (instead of permute + cast + scatter and gather + permute + cast)."""
+
+    @staticmethod
+    def forward(ctx, logits, perm, B, N):
+        C = logits.shape[1]
+        out = torch.empty(B, C, N, dtype=torch.float32, device=logits.device)
+        _lib.call("fs_logits_out", logits, logits, _lib.dtype_code(logits), logits.stride(0), perm, B, N, C, out)
+        ctx.perm, ctx.shape, ctx.dtype = perm, (B, N, C), logits.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, N, C = ctx.shape
+        g = g.float().contiguous()
+        d = torch.empty(B * N, C, dtype=ctx.dtype, device=g.device)
+        _lib.call("fs_logits_out_bwd", g, g, ctx.perm, B, N, C, d, _lib.dtype_code(d), d.stride(0))
+        return d, None, None, None
+
+
+def logits_out(logits_pm, perm, B, N):
+    """logits_pm (B*N, C) fp32 / bf16 with unit channel stride; perm (B, N) int64 or None."""
+    if not logits_pm.is_cuda or logits_pm.dtype not in (torch.float32, torch.bfloat16) or logits_pm.stride(1) != 1:
+        y = logits_pm.view(B, N, -1).permute(0, 2, 1).float()
+        if perm is None:
+            return y
+        return torch.empty_like(y).scatter(2, perm.unsqueeze(1).expand_as(y), y)
+    return _LogitsOutFn.apply(logits_pm, perm.contiguous() if perm is not None else None, B, N)
+
+
 _ones_cache = {}
 
 

@@ -398,6 +398,16 @@ int fs_split_cast(int device, fs_stream_t stream, int n, void* const* dsts, cons
 int fs_multi_copy_f32(int device, fs_stream_t stream, int n, const void* const* srcs, void* const* dsts,
                       const long long* counts);
 
+/*
+ * Network output: point-major logits [B*N, C] (fp32 / bf16, row pitch ld) of the internally re-ordered cloud ->
+ * out [B, C, N] fp32 in the caller's point order, out[b, c, perm[b,n]] = logits[b*N + n, c] (perm [B,N] int64, nullable =
+ * identity): the `B x classes x N` tensor the reference's forward returns (models/dgcnn.py:162). _bwd is the adjoint.
+ */
+int fs_logits_out(int device, fs_stream_t stream, const void* logits, int dtype, int ld, const long long* perm, int B, int N,
+                  int C, float* out);
+int fs_logits_out_bwd(int device, fs_stream_t stream, const float* g, const long long* perm, int B, int N, int C,
+                      void* dlogits, int dtype, int ld);
+
 /* ---------------------------------------------------------------- Chamfer ------------------ */
 
 /*

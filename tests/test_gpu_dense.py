@@ -202,3 +202,22 @@ def test_pool_gemm_ties_and_non_finite_rows(lib, monkeypatch):
     assert int(arg[0].max()) == 0 and int(arg[0].min()) == 0
     assert (arg[1] == 40).all()
     assert int(arg[2].min()) >= 0 and int(arg[2].max()) < N
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_logits_out_matches_permute_scatter(lib, dtype):
+    B, N, C = 3, 1000, 4
+    gen = torch.Generator().manual_seed(6)
+    logits = torch.randn(B * N, C, generator=gen).to(DEV).to(dtype)
+    perm = torch.stack([torch.randperm(N, generator=gen) for _ in range(B)]).to(DEV)
+    g = torch.randn(B, C, N, generator=gen).to(DEV)
+    for p in (perm, None):
+        a = logits.clone().requires_grad_(True)
+        out = ops.logits_out(a, p, B, N)
+        out.backward(g)
+        b = logits.clone().requires_grad_(True)
+        y = b.view(B, N, C).permute(0, 2, 1).float()
+        ref = y if p is None else torch.empty_like(y).scatter(2, p.unsqueeze(1).expand_as(y), y)
+        ref.backward(g)
+        assert torch.equal(out, ref)
+        assert torch.equal(a.grad, b.grad)
