@@ -39,6 +39,25 @@ template <typename T> __device__ __forceinline__ void st_from_float(T* p, float 
 template <> __device__ __forceinline__ void st_from_float<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+__device__ __forceinline__ void load_quad(const float* p, float* f) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+__device__ __forceinline__ void load_quad(const __nv_bfloat16* p, float* f) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const float2 a = __bfloat1622float2(hh[0]), b = __bfloat1622float2(hh[1]);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ void store_quad(float* p, const float* f) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+__device__ __forceinline__ void store_quad(__nv_bfloat16* p, const float* f) {
+    uint2 v;
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&v);
+    hh[0] = __floats2bfloat162_rn(f[0], f[1]);
+    hh[1] = __floats2bfloat162_rn(f[2], f[3]);
+    *reinterpret_cast<uint2*>(p) = v;
+}
+
 // 16-byte chunk of a row: 8 bf16 or 4 fp32 values
 template <typename T> struct Chunk;
 template <> struct Chunk<__nv_bfloat16> {
@@ -390,6 +409,190 @@ __global__ void logits_out_bwd_kernel(const float* __restrict__ g, const long lo
         const float* gb = g + b * C * N + src;
         T* row = dlogits + e * ld;
         for (int c = 0; c < C; ++c) st_from_float(row + c, gb[(long long)c * N]);
+    }
+}
+
+// ---- last layer of the segmentation head fused with the network output (models/dgcnn.py:137, 160-162): a 1x1 conv to
+// `num_classes` (<= 8) channels with bias, no BatchNorm, written straight as (B, classes, N) fp32 in the caller's point
+// order. As library calls this is three GEMMs with a 4-wide dimension (16 + 12 + 16 us at P = 65536, C_in = 128) plus
+// the un-sort / transpose / cast passes; here one pass over H each way.
+// Forward: a block stages 128 rows of H in shared memory with coalesced 16-byte loads (rows padded by one chunk, so the
+// per-point reads below are bank-conflict-free), then one THREAD per point forms its NOUT sums - no cross-lane reduction;
+// the weights are shared-memory broadcasts.
+template <typename T, int NOUT, int CIN>
+__global__ void __launch_bounds__(128)
+final_linear_fwd_kernel(const T* __restrict__ h, int ld, const float* __restrict__ w, const float* __restrict__ bias,
+                        const long long* __restrict__ perm, int B, int N, float* __restrict__ out) {
+    constexpr int V = Chunk<T>::N;              // values per 16-byte chunk
+    constexpr int RS = CIN + V;                 // padded row stride (elements)
+    extern __shared__ __align__(16) unsigned char ff_smem[];
+    T* h_s = reinterpret_cast<T*>(ff_smem);                                         // [128][RS]
+    float* w_s = reinterpret_cast<float*>(ff_smem + (size_t)128 * RS * sizeof(T));   // [NOUT][CIN]
+    const long long total = (long long)B * N;
+    const long long e0 = (long long)blockIdx.x * 128;
+    const int rows = (int)(total - e0 < 128 ? total - e0 : 128);
+    for (int i = threadIdx.x; i < NOUT * CIN; i += blockDim.x) w_s[i] = __ldg(w + i);
+    {   // all of a thread's chunks are requested before the first one is stored (no load -> store -> load chain)
+        constexpr int PER = 128 * (CIN / V) / 128;
+        uint4 v[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = threadIdx.x + u * 128;
+            const int p = i / (CIN / V), q = i - p * (CIN / V);
+            v[u] = p < rows ? __ldg(reinterpret_cast<const uint4*>(h + (e0 + p) * ld + q * V)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = threadIdx.x + u * 128;
+            const int p = i / (CIN / V), q = i - p * (CIN / V);
+            *reinterpret_cast<uint4*>(h_s + p * RS + q * V) = v[u];
+        }
+    }
+    __syncthreads();
+    const int p = threadIdx.x;
+    if (p >= rows) return;
+    float acc[NOUT];
+#pragma unroll
+    for (int c = 0; c < NOUT; ++c) acc[c] = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll 4
+    for (int q = 0; q < CIN / V; ++q) {
+        float hv[V];
+        Chunk<T>::load(h_s + p * RS + q * V, hv);
+#pragma unroll
+        for (int c = 0; c < NOUT; ++c)
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[c] = fmaf(w_s[c * CIN + q * V + i], hv[i], acc[c]);
+    }
+    const long long e = e0 + p;
+    const long long b = e / N;
+    const long long dst = perm ? perm[e] : e - b * N;
+#pragma unroll
+    for (int c = 0; c < NOUT; ++c) out[(b * NOUT + c) * N + dst] = acc[c];
+}
+
+// Backward: a block stages TILE rows of H and their (gathered) output gradients in shared memory; dH = G W is written per
+// point, dW = G^T H and dbias = sum G leave as per-block partials (summed by final_linear_red_kernel in block order:
+// deterministic).
+constexpr int FL_TILE = 128;
+template <typename T, int NOUT, int CIN>
+__global__ void __launch_bounds__(256)
+final_linear_bwd_kernel(const T* __restrict__ h, int ld, const float* __restrict__ w, const float* __restrict__ g,
+                        const long long* __restrict__ perm, int B, int N, T* __restrict__ dh, int ld_dh,
+                        float* __restrict__ part /* [grid][NOUT * CIN + NOUT] */) {
+    constexpr int V = Chunk<T>::N;
+    extern __shared__ __align__(16) unsigned char fl_smem[];
+    T* h_s = reinterpret_cast<T*>(fl_smem);                                         // [TILE][CIN]
+    float* w_s = reinterpret_cast<float*>(fl_smem + (size_t)FL_TILE * CIN * sizeof(T));   // [NOUT][CIN]
+    float* g_s = w_s + NOUT * CIN;                                                  // [TILE][NOUT]
+    const long long total = (long long)B * N;
+    const long long e0 = (long long)blockIdx.x * FL_TILE;
+    const int rows = (int)(total - e0 < FL_TILE ? total - e0 : FL_TILE);
+    for (int i = threadIdx.x; i < NOUT * CIN; i += blockDim.x) w_s[i] = __ldg(w + i);
+    {   // all of a thread's chunks are requested before the first one is stored (no load -> store -> load chain)
+        constexpr int PER = FL_TILE * (CIN / V) / 256;
+        uint4 v[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = threadIdx.x + u * 256;
+            const int p = i / (CIN / V), q = i - p * (CIN / V);
+            v[u] = p < rows ? __ldg(reinterpret_cast<const uint4*>(h + (e0 + p) * ld + q * V)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = threadIdx.x + u * 256;
+            const int p = i / (CIN / V), q = i - p * (CIN / V);
+            *reinterpret_cast<uint4*>(h_s + p * CIN + q * V) = v[u];
+        }
+    }
+    for (int i = threadIdx.x; i < FL_TILE * NOUT; i += blockDim.x) {
+        const int p = i / NOUT, c = i - p * NOUT;
+        float v = 0.f;
+        if (p < rows) {
+            const long long e = e0 + p, b = e / N;
+            const long long src = perm ? perm[e] : e - b * N;
+            v = __ldg(g + (b * NOUT + c) * N + src);
+        }
+        g_s[i] = v;
+    }
+    __syncthreads();
+    // dH: one 16-byte chunk per thread and step, consecutive threads on consecutive chunks of a row (coalesced stores)
+    for (int i = threadIdx.x; i < rows * (CIN / V); i += blockDim.x) {
+        const int p = i / (CIN / V), q = i - p * (CIN / V);
+        float dv[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) dv[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NOUT; ++c) {
+            const float gc = g_s[p * NOUT + c];
+#pragma unroll
+            for (int j = 0; j < V; ++j) dv[j] = fmaf(gc, w_s[c * CIN + q * V + j], dv[j]);
+        }
+        Chunk<T>::store(dh + (e0 + p) * ld_dh + q * V, dv);
+    }
+    // dW, dbias partials of this tile: a thread owns two adjacent input channels for ALL classes over a quarter (CIN 128)
+    // or half (CIN 256) of the tile's points - one 4- or 8-byte shared-memory read of H per point feeds 2 * NOUT FMAs -
+    // then the point groups are summed in a fixed order through shared memory (the H tile is no longer needed).
+    constexpr int PAIRS = CIN / 2, PG = 256 / PAIRS, PPG = FL_TILE / PG;
+    const int ip = threadIdx.x % PAIRS, pg = threadIdx.x / PAIRS;
+    float acc[NOUT][2];
+#pragma unroll
+    for (int c = 0; c < NOUT; ++c) { acc[c][0] = 0.f; acc[c][1] = 0.f; }
+#pragma unroll 4
+    for (int p = pg * PPG; p < (pg + 1) * PPG; ++p) {
+        float h0, h1;
+        if (sizeof(T) == 2) {
+            const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(h_s + p * CIN + 2 * ip));
+            h0 = hv.x; h1 = hv.y;
+        } else {
+            const float2 hv = *reinterpret_cast<const float2*>(h_s + p * CIN + 2 * ip);
+            h0 = hv.x; h1 = hv.y;
+        }
+#pragma unroll
+        for (int c = 0; c < NOUT; ++c) {
+            const float gc = g_s[p * NOUT + c];
+            acc[c][0] = fmaf(gc, h0, acc[c][0]);
+            acc[c][1] = fmaf(gc, h1, acc[c][1]);
+        }
+    }
+    __syncthreads();                                   // every read of the H tile is done: reuse it as scratch
+    float* red = reinterpret_cast<float*>(fl_smem);    // [PG][NOUT][CIN]  (PG * NOUT * CIN * 4 <= TILE * CIN * sizeof(T))
+#pragma unroll
+    for (int c = 0; c < NOUT; ++c) {
+        red[(pg * NOUT + c) * CIN + 2 * ip] = acc[c][0];
+        red[(pg * NOUT + c) * CIN + 2 * ip + 1] = acc[c][1];
+    }
+    __syncthreads();
+    float* pb = part + (long long)blockIdx.x * (NOUT * CIN + NOUT);
+    for (int o = threadIdx.x; o < NOUT * CIN; o += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < PG; ++q) v += red[q * NOUT * CIN + o];
+        pb[o] = v;
+    }
+    if (threadIdx.x < NOUT) {
+        float a = 0.f;
+        for (int p = 0; p < FL_TILE; ++p) a += g_s[p * NOUT + threadIdx.x];
+        pb[NOUT * CIN + threadIdx.x] = a;
+    }
+}
+// out[t] = sum over the G partial rows, block = 32 outputs x 32 partial groups (fixed order)
+__global__ void __launch_bounds__(1024)
+final_linear_red_kernel(const float* __restrict__ part, int G, int n, float* __restrict__ out) {
+    __shared__ float red[32][33];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    float v = 0.f;
+    if (t < n) {
+#pragma unroll 4
+        for (int q = grp; q < G; q += 32) v += __ldg(part + (long long)q * n + t);
+    }
+    red[grp][lane] = v;
+    __syncthreads();
+    if (grp == 0 && t < n) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) a += red[q][lane];
+        out[t] = a;
     }
 }
 
@@ -758,6 +961,88 @@ extern "C" int fs_logits_out_bwd(int device, fs_stream_t stream_, const float* g
     const int grid = (int)(fs_div_up(total, 256) < (long long)FS_NUM_SMS * 8 ? fs_div_up(total, 256) : (long long)FS_NUM_SMS * 8);
     if (dtype == FS_BF16) logits_out_bwd_kernel<<<grid, 256, 0, stream>>>(g, perm, B, N, C, (__nv_bfloat16*)dlogits, ld);
     else logits_out_bwd_kernel<<<grid, 256, 0, stream>>>(g, perm, B, N, C, (float*)dlogits, ld);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+namespace {
+template <typename T, int NOUT, int CIN>
+int final_fwd_t(cudaStream_t stream, const T* h, int ld, const float* w, const float* bias, const long long* perm, int B, int N,
+                float* out) {
+    const long long total = (long long)B * N;
+    const size_t smem = (size_t)128 * (CIN + Chunk<T>::N) * sizeof(T) + (size_t)NOUT * CIN * 4;
+    FS_CUDA_TRY(cudaFuncSetAttribute(final_linear_fwd_kernel<T, NOUT, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    final_linear_fwd_kernel<T, NOUT, CIN><<<(unsigned)fs_div_up(total, 128), 128, smem, stream>>>(h, ld, w, bias, perm, B, N, out);
+    return FS_OK;
+}
+template <typename T, int NOUT, int CIN>
+int final_bwd_t(cudaStream_t stream, const T* h, int ld, const float* w, const float* g, const long long* perm, int B, int N,
+                T* dh, int ld_dh, float* part, float* dwb) {
+    const long long total = (long long)B * N;
+    const int grid = (int)fs_div_up(total, FL_TILE);
+    const size_t smem = (size_t)FL_TILE * CIN * sizeof(T) + (size_t)NOUT * CIN * 4 + (size_t)FL_TILE * NOUT * 4;
+    FS_CUDA_TRY(cudaFuncSetAttribute(final_linear_bwd_kernel<T, NOUT, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    final_linear_bwd_kernel<T, NOUT, CIN><<<grid, 256, smem, stream>>>(h, ld, w, g, perm, B, N, dh, ld_dh, part);
+    const int n = NOUT * CIN + NOUT;
+    final_linear_red_kernel<<<(n + 31) / 32, 1024, 0, stream>>>(part, grid, n, dwb);
+    return FS_OK;
+}
+bool final_ok(int C_in, int C_out) {
+    return (C_in == 128 && (C_out == 2 || C_out == 4 || C_out == 8)) || (C_in == 256 && (C_out == 2 || C_out == 4));
+}
+}  // namespace
+
+// one dispatch for both directions: FL_GO(fn, args...) instantiates fn<T, NOUT, CIN>
+#define FL_DISPATCH(FN, ...)                                                                                        \
+    do {                                                                                                            \
+        if (C_in == 128 && C_out == 2) rc = FN<TT, 2, 128>(__VA_ARGS__);                                             \
+        else if (C_in == 128 && C_out == 4) rc = FN<TT, 4, 128>(__VA_ARGS__);                                        \
+        else if (C_in == 128 && C_out == 8) rc = FN<TT, 8, 128>(__VA_ARGS__);                                        \
+        else if (C_in == 256 && C_out == 2) rc = FN<TT, 2, 256>(__VA_ARGS__);                                        \
+        else rc = FN<TT, 4, 256>(__VA_ARGS__);                                                                       \
+    } while (0)
+
+extern "C" int fs_final_linear_supported(int C_in, int C_out) { return final_ok(C_in, C_out) ? 1 : 0; }
+extern "C" size_t fs_final_linear_ws_floats(long long rows, int C_in, int C_out) {
+    if (rows <= 0) return 0;
+    return (size_t)fs_div_up(rows, FL_TILE) * (size_t)(C_out * C_in + C_out);
+}
+
+extern "C" int fs_final_linear_fwd(int device, fs_stream_t stream_, const void* h, int dtype, int ld, const float* w,
+                                   const float* bias, const long long* perm, int B, int N, int C_in, int C_out, float* out) {
+    if (!h || !w || !out || B <= 0 || N <= 0 || ld < C_in) return FS_ERR_BAD_ARG;
+    if (!final_ok(C_in, C_out) || ld % 8 || ((uintptr_t)h & 15)) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = FS_OK;
+    if (dtype == FS_BF16) {
+        using TT = __nv_bfloat16;
+        FL_DISPATCH(final_fwd_t, stream, (const TT*)h, ld, w, bias, perm, B, N, out);
+    } else {
+        using TT = float;
+        FL_DISPATCH(final_fwd_t, stream, (const TT*)h, ld, w, bias, perm, B, N, out);
+    }
+    if (rc != FS_OK) return rc;
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_final_linear_bwd(int device, fs_stream_t stream_, const void* h, int dtype, int ld, const float* w, const float* g,
+                                   const long long* perm, int B, int N, int C_in, int C_out, void* dh, int ld_dh, float* ws,
+                                   float* dw_db /* [C_out * C_in] dW, then [C_out] dbias */) {
+    if (!h || !w || !g || !dh || !ws || !dw_db || B <= 0 || N <= 0 || ld < C_in || ld_dh < C_in) return FS_ERR_BAD_ARG;
+    if (!final_ok(C_in, C_out) || ld % 8 || ld_dh % 8 || ((uintptr_t)h & 15) || ((uintptr_t)dh & 15)) return FS_ERR_UNSUPPORTED;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = FS_OK;
+    if (dtype == FS_BF16) {
+        using TT = __nv_bfloat16;
+        FL_DISPATCH(final_bwd_t, stream, (const TT*)h, ld, w, g, perm, B, N, (TT*)dh, ld_dh, ws, dw_db);
+    } else {
+        using TT = float;
+        FL_DISPATCH(final_bwd_t, stream, (const TT*)h, ld, w, g, perm, B, N, (TT*)dh, ld_dh, ws, dw_db);
+    }
+    if (rc != FS_OK) return rc;
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
 }

@@ -387,7 +387,12 @@ class DGCNNSeg(DGCNNBase):
             h = seg0.norm_act_pm(local, rowbias=per_cloud, rows_per_cloud=N)
             h = self.segmentation[1].forward_pm(h)
             h = self.segmentation[2].forward_pm(h)
-            logits = self.segmentation[3].forward_pm(h)                          # (B*N, classes)
+            last = self.segmentation[3]
+            if (last.norm is None and not last.has_activation and h.is_contiguous()
+                    and ops.final_linear_supported(h, last.weight_matrix())):
+                # classes-wide 1x1 conv + bias written straight as (B, classes, N) fp32 in the caller's point order
+                return ops.final_linear_out(h, last.weight_matrix(), last.conv.bias, self._perm, B, N)
+            logits = last.forward_pm(h)                                          # (B*N, classes)
             return ops.logits_out(logits, self._perm, B, N)          # (B, classes, N) fp32 in the caller's point order
 
 

@@ -847,6 +847,48 @@ def logits_out(logits_pm, perm, B, N):
     return _LogitsOutFn.apply(logits_pm, perm.contiguous() if perm is not None else None, B, N)
 
 
+class _FinalLinearFn(torch.autograd.Function):
+    """Last layer of the segmentation head (1x1 conv to num_classes channels + bias, no BatchNorm) fused with the network
+    output: (B*N, C_in) -> (B, classes, N) fp32 in the caller's point order, one pass over H each way (csrc/heads.cu);
+    as library calls it is three GEMMs with a 4-wide dimension plus the un-sort / transpose / cast passes."""
+
+    @staticmethod
+    def forward(ctx, h, w, bias, perm, B, N):
+        w32 = w.detach().float().contiguous()
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        C_out, C_in = w32.shape
+        out = torch.empty(B, C_out, N, dtype=torch.float32, device=h.device)
+        _lib.call("fs_final_linear_fwd", h, h, _lib.dtype_code(h), h.stride(0), w32, b32, perm, B, N, C_in, C_out, out)
+        ctx.save_for_backward(h, w32)
+        ctx.perm, ctx.dims, ctx.w_dtype, ctx.has_bias = perm, (B, N, C_in, C_out), w.dtype, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w32 = ctx.saved_tensors
+        B, N, C_in, C_out = ctx.dims
+        g = g.float().contiguous()
+        dh = torch.empty(B * N, C_in, dtype=h.dtype, device=h.device)
+        ws = _workspace(4 * _lib.load().fs_final_linear_ws_floats(B * N, C_in, C_out), h.device, "final_linear")
+        dwdb = torch.empty(C_out * C_in + C_out, dtype=torch.float32, device=h.device)
+        _lib.call("fs_final_linear_bwd", h, h, _lib.dtype_code(h), h.stride(0), w32, g, ctx.perm, B, N, C_in, C_out, dh,
+                  dh.stride(0), ws, dwdb)
+        dw = dwdb[:C_out * C_in].view(C_out, C_in).to(ctx.w_dtype)
+        db = dwdb[C_out * C_in:].to(ctx.w_dtype) if ctx.has_bias else None
+        return dh, dw, db, None, None, None
+
+
+def final_linear_supported(h, w):
+    return (h.is_cuda and h.dtype in (torch.float32, torch.bfloat16) and h.dim() == 2 and h.stride(1) == 1
+            and h.stride(0) % 8 == 0 and h.data_ptr() % 16 == 0 and w.dim() == 2 and w.shape[1] == h.shape[1]
+            and bool(_lib.load().fs_final_linear_supported(w.shape[1], w.shape[0])))
+
+
+def final_linear_out(h, w, bias, perm, B, N):
+    """h (B*N, C_in), w (classes, C_in), bias (classes,) or None, perm (B, N) int64 or None -> (B, classes, N) fp32."""
+    return _FinalLinearFn.apply(h, w, bias, perm.contiguous() if perm is not None else None, B, N)
+
+
 _ones_cache = {}
 
 

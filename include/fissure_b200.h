@@ -408,6 +408,21 @@ int fs_logits_out(int device, fs_stream_t stream, const void* logits, int dtype,
 int fs_logits_out_bwd(int device, fs_stream_t stream, const float* g, const long long* perm, int B, int N, int C,
                       void* dlogits, int dtype, int ld);
 
+/*
+ * Last layer of the segmentation head fused with the network output (models/dgcnn.py:137, 160-162): 1x1 conv to
+ * C_out = num_classes (2, 4 or 8) channels with bias, no BatchNorm; h [B*N, C_in] (C_in 128, or 256 with C_out <= 4; fp32 / bf16), w [C_out,
+ * C_in] f32, out [B, C_out, N] f32 in the caller's point order (perm as fs_logits_out). Backward: dh [B*N, C_in] in h's dtype,
+ * dw_db [C_out*C_in + C_out] f32 = dW [C_out, C_in] followed by dbias [C_out]; ws = fs_final_linear_ws_floats(B*N, ...)
+ * floats of scratch (per-block partials, summed in block order: deterministic).
+ */
+int fs_final_linear_supported(int C_in, int C_out);
+size_t fs_final_linear_ws_floats(long long rows, int C_in, int C_out);
+int fs_final_linear_fwd(int device, fs_stream_t stream, const void* h, int dtype, int ld, const float* w, const float* bias,
+                        const long long* perm, int B, int N, int C_in, int C_out, float* out);
+int fs_final_linear_bwd(int device, fs_stream_t stream, const void* h, int dtype, int ld, const float* w, const float* g,
+                        const long long* perm, int B, int N, int C_in, int C_out, void* dh, int ld_dh, float* ws,
+                        float* dw_db);
+
 /* ---------------------------------------------------------------- Chamfer ------------------ */
 
 /*

@@ -221,3 +221,30 @@ def test_logits_out_matches_permute_scatter(lib, dtype):
         ref.backward(g)
         assert torch.equal(out, ref)
         assert torch.equal(a.grad, b.grad)
+
+
+@pytest.mark.parametrize("dtype,C_in,C_out,N", [(torch.float32, 128, 4, 1000), (torch.bfloat16, 128, 4, 2048),
+                                               (torch.float32, 256, 2, 300), (torch.bfloat16, 128, 8, 777)])
+def test_final_linear_out_matches_torch(lib, dtype, C_in, C_out, N):
+    """Last head layer fused with the output (classes-wide conv + bias -> (B, classes, N) fp32 in the caller's order)."""
+    B = 3
+    gen = torch.Generator().manual_seed(C_in + C_out + N)
+    h = torch.randn(B * N, C_in, generator=gen).to(DEV).to(dtype)
+    w = (torch.randn(C_out, C_in, generator=gen) / C_in ** 0.5).to(DEV)
+    bias = torch.randn(C_out, generator=gen).to(DEV)
+    perm = torch.stack([torch.randperm(N, generator=gen) for _ in range(B)]).to(DEV)
+    g = torch.randn(B, C_out, N, generator=gen).to(DEV)
+    for p in (perm, None):
+        a, wa, ba = h.clone().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+        assert ops.final_linear_supported(a, wa)
+        out = ops.final_linear_out(a, wa, ba, p, B, N)
+        out.backward(g)
+        b, wb, bb = h.double().requires_grad_(True), w.double().requires_grad_(True), bias.double().requires_grad_(True)
+        y = (b @ wb.t() + bb).view(B, N, C_out).permute(0, 2, 1)
+        ref = y if p is None else torch.empty_like(y).scatter(2, p.unsqueeze(1).expand_as(y), y)
+        ref.backward(g.double())
+        assert_close(out, ref.float(), 1e-5, 1e-5, "logits")
+        gt = 1e-5 if dtype == torch.float32 else 1e-2          # dH is stored in h's dtype
+        assert rel_err(a.grad.float(), b.grad.float()) < gt
+        assert rel_err(wa.grad, wb.grad.float()) < 1e-5
+        assert rel_err(ba.grad, bb.grad.float()) < 1e-5
