@@ -596,6 +596,20 @@ final_linear_red_kernel(const float* __restrict__ part, int G, int n, float* __r
     }
 }
 
+// ---- EdgeConv weight table: [W1 ; W2 - W1] (2Cp x C) from the conv weight W = [W1 | W2] (Cp x 2C), and the adjoint
+__global__ void edge_weight_table_kernel(const float* __restrict__ w, int Cp, int C, float* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 2 * Cp * C) return;
+    const int r = e / C, c = e - r * C;
+    out[e] = r < Cp ? w[r * 2 * C + c] : w[(r - Cp) * 2 * C + C + c] - w[(r - Cp) * 2 * C + c];
+}
+__global__ void edge_weight_table_bwd_kernel(const float* __restrict__ g, int Cp, int C, float* __restrict__ dw) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 2 * Cp * C) return;
+    const int r = e / (2 * C), c = e - r * 2 * C;
+    dw[e] = c < C ? g[r * C + c] - g[(Cp + r) * C + c] : g[(Cp + r) * C + (c - C)];
+}
+
 // ---- gradient bucket: up to 32 fp32 tensors copied into their slices of a flat buffer by ONE launch. The table of
 // (source, destination, element count) travels as a kernel parameter, so nothing is staged through device memory.
 struct MultiCopy {
@@ -1043,6 +1057,21 @@ extern "C" int fs_final_linear_bwd(int device, fs_stream_t stream_, const void* 
         FL_DISPATCH(final_bwd_t, stream, (const TT*)h, ld, w, g, perm, B, N, (TT*)dh, ld_dh, ws, dw_db);
     }
     if (rc != FS_OK) return rc;
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_edge_weight_table(int device, fs_stream_t stream_, const float* w, int Cp, int C, float* out) {
+    if (!w || !out || Cp <= 0 || C <= 0) return FS_ERR_BAD_ARG;
+    FS_ENTER(device);
+    edge_weight_table_kernel<<<(2 * Cp * C + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(w, Cp, C, out);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+extern "C" int fs_edge_weight_table_bwd(int device, fs_stream_t stream_, const float* g, int Cp, int C, float* dw) {
+    if (!g || !dw || Cp <= 0 || C <= 0) return FS_ERR_BAD_ARG;
+    FS_ENTER(device);
+    edge_weight_table_bwd_kernel<<<(2 * Cp * C + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(g, Cp, C, dw);
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
 }

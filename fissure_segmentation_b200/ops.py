@@ -973,15 +973,18 @@ def table_gemm(x, w, tf32=False):
 class _EdgeWeightFn(torch.autograd.Function):
     """[W1 ; W2 - W1] (2Cp, C) from the EdgeConv weight W = [W1 | W2] (Cp, 2C) (models/dgcnn.py:36 column order).
     Written as `cat([w[:, :C], w[:, C:] - w[:, :C]])` autograd replays slices, a subtraction and a concatenation:
-    4 small kernels forward and 9 backward per layer; here it is 2 + 2."""
+    4 small kernels forward and 9 backward per layer; here it is 1 + 1."""
 
     @staticmethod
     def forward(ctx, w, C):
         Cp = w.shape[0]
         wf = w if w.dtype == torch.float32 else w.float()
         out = torch.empty(2 * Cp, C, dtype=torch.float32, device=w.device)
-        out[:Cp].copy_(wf[:, :C])
-        torch.sub(wf[:, C:], wf[:, :C], out=out[Cp:])
+        if wf.is_cuda and wf.is_contiguous():
+            _lib.call("fs_edge_weight_table", wf, wf, Cp, C, out)
+        else:
+            out[:Cp].copy_(wf[:, :C])
+            torch.sub(wf[:, C:], wf[:, :C], out=out[Cp:])
         ctx.C = C
         ctx.w_dtype = w.dtype
         return out
@@ -992,8 +995,11 @@ class _EdgeWeightFn(torch.autograd.Function):
         Cp = g.shape[0] // 2
         g = g.float()
         dw = torch.empty(Cp, 2 * C, dtype=torch.float32, device=g.device)
-        torch.sub(g[:Cp], g[Cp:], out=dw[:, :C])        # dW1 = g_a - g_b
-        dw[:, C:].copy_(g[Cp:])                         # dW2 = g_b
+        if g.is_cuda and g.is_contiguous():
+            _lib.call("fs_edge_weight_table_bwd", g, g, Cp, C, dw)
+        else:
+            torch.sub(g[:Cp], g[Cp:], out=dw[:, :C])        # dW1 = g_a - g_b
+            dw[:, C:].copy_(g[Cp:])                         # dW2 = g_b
         return dw.to(ctx.w_dtype), None
 
 

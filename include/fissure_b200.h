@@ -423,6 +423,14 @@ int fs_final_linear_bwd(int device, fs_stream_t stream, const void* h, int dtype
                         const long long* perm, int B, int N, int C_in, int C_out, void* dh, int ld_dh, float* ws,
                         float* dw_db);
 
+/*
+ * EdgeConv weight table: out [2Cp, C] f32 = [W1 ; W2 - W1] from the conv weight w [Cp, 2C] f32 = [W1 | W2] (column order of
+ * models/dgcnn.py:36: neighbour difference first, centre second) - the right-hand side of the per-point table GEMM - and
+ * the adjoint dw [Cp, 2C] from g [2Cp, C].
+ */
+int fs_edge_weight_table(int device, fs_stream_t stream, const float* w, int Cp, int C, float* out);
+int fs_edge_weight_table_bwd(int device, fs_stream_t stream, const float* g, int Cp, int C, float* dw);
+
 /* ---------------------------------------------------------------- Chamfer ------------------ */
 
 /*
