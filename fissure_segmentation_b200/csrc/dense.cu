@@ -116,15 +116,20 @@ bn_act_apply_kernel(const T* __restrict__ x, int ld, long long rows, int C, cons
                     const float* __restrict__ coef, const FsBnFin fin, float slope, OT* __restrict__ out, int ld_out) {
     constexpr int V = Vec<T>::N;
     RowMap m(C, V);
+    extern __shared__ float ba_coef[];          // [3][C] when the finalisation is folded in: one channel per thread, once
+    if (fin.stats) {                            // per block (the fp64 divide / sqrt per channel is not free)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float mu1, inv, sc1, be1;
+            fs_bn_fin_channel(fin, c, C, blockIdx.x == 0, mu1, inv, sc1, be1);
+            ba_coef[c] = mu1; ba_coef[C + c] = sc1; ba_coef[2 * C + c] = be1;
+        }
+        __syncthreads();
+    }
     for (int cc = m.c0; cc < C; cc += m.tpr * V) {
         float mu[V], sc[V], be[V];
-        if (fin.stats) {        // coefficients straight from the statistics; block 0, first row group publishes them
-            const bool publish = blockIdx.x == 0 && m.r == 0;
+        if (fin.stats) {
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                float inv;
-                fs_bn_fin_channel(fin, cc + i, C, publish, mu[i], inv, sc[i], be[i]);
-            }
+            for (int i = 0; i < V; ++i) { mu[i] = ba_coef[cc + i]; sc[i] = ba_coef[C + cc + i]; be[i] = ba_coef[2 * C + cc + i]; }
         } else {
 #pragma unroll
             for (int i = 0; i < V; ++i) { mu[i] = __ldg(coef + cc + i); sc[i] = __ldg(coef + 2 * C + cc + i); be[i] = __ldg(coef + 3 * C + cc + i); }
@@ -453,7 +458,8 @@ static int bn_act_apply_launch(int device, fs_stream_t stream_, const void* x, i
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int grid = dn_grid(rows, rows_per_pass(C, vec));
-#define GO(T, OT) bn_act_apply_kernel<<<grid, DN_THREADS, 0, stream>>>((const T*)x, ld, rows, C, rowbias, N, coef, fin, slope, (OT*)out, ld_out)
+    const size_t smem = fin.stats ? (size_t)3 * C * sizeof(float) : 0;
+#define GO(T, OT) bn_act_apply_kernel<<<grid, DN_THREADS, smem, stream>>>((const T*)x, ld, rows, C, rowbias, N, coef, fin, slope, (OT*)out, ld_out)
     if (dtype == FS_BF16 && out_dtype == FS_BF16) GO(__nv_bfloat16, __nv_bfloat16);
     else if (dtype == FS_BF16) GO(__nv_bfloat16, float);
     else if (out_dtype == FS_BF16) GO(float, __nv_bfloat16);

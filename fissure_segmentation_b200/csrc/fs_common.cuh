@@ -139,11 +139,15 @@ struct FsBnFin {
 };
 __device__ __forceinline__ void fs_bn_fin_channel(const FsBnFin& f, int c, int C, bool publish, float& mean_f, float& invstd,
                                                   float& scale, float& beta) {
-    const double m1 = f.stats[c] / f.count;
-    double var = f.stats[C + c] / f.count - m1 * m1;
+    // fp64 only where it matters (E[y^2] - mean^2 cancels); the reciprocal square root is taken in fp32 (correctly rounded
+    // sqrtf and division: every block derives bit-identical coefficients) - the fp64 divide / sqrt routines cost hundreds
+    // of instructions per channel
+    const double ic = 1.0 / f.count;
+    const double m1 = f.stats[c] * ic;
+    double var = f.stats[C + c] * ic - m1 * m1;
     if (var < 0.0) var = 0.0;
     const double mean = m1 + f.stats[2 * C + c];
-    invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+    invstd = 1.0f / sqrtf((float)var + f.eps);
     mean_f = (float)mean;
     scale = __ldg(f.gamma + c) * invstd;
     beta = __ldg(f.beta + c);
