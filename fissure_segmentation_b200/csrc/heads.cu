@@ -610,6 +610,30 @@ __global__ void edge_weight_table_bwd_kernel(const float* __restrict__ g, int Cp
     dw[e] = c < C ? g[r * C + c] - g[(Cp + r) * C + c] : g[(Cp + r) * C + (c - C)];
 }
 
+// ---- out[t] = sum_s part[s, t]: the partial results of a chunked (batched) weight-gradient GEMM, fixed order over s.
+// Threads across t (coalesced), S / SG partials per thread in SG interleaved groups, combined through shared memory.
+template <int SG>
+__global__ void __launch_bounds__(256)
+sum_leading_kernel(const float* __restrict__ part, int S, long long n, float* __restrict__ out) {
+    __shared__ float red[SG][256 / SG];
+    constexpr int TPB = 256 / SG;                     // outputs per block
+    const int lane_t = threadIdx.x % TPB, grp = threadIdx.x / TPB;
+    const long long t = (long long)blockIdx.x * TPB + lane_t;
+    float v = 0.f;
+    if (t < n) {
+#pragma unroll 4
+        for (int q = grp; q < S; q += SG) v += __ldg(part + (long long)q * n + t);
+    }
+    red[grp][lane_t] = v;
+    __syncthreads();
+    if (grp == 0 && t < n) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < SG; ++q) a += red[q][lane_t];
+        out[t] = a;
+    }
+}
+
 // ---- gradient bucket: up to 32 fp32 tensors copied into their slices of a flat buffer by ONE launch. The table of
 // (source, destination, element count) travels as a kernel parameter, so nothing is staged through device memory.
 struct MultiCopy {
@@ -1072,6 +1096,17 @@ extern "C" int fs_edge_weight_table_bwd(int device, fs_stream_t stream_, const f
     if (!g || !dw || Cp <= 0 || C <= 0) return FS_ERR_BAD_ARG;
     FS_ENTER(device);
     edge_weight_table_bwd_kernel<<<(2 * Cp * C + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(g, Cp, C, dw);
+    FS_RETURN_IF_LAUNCH_FAILED();
+    return FS_OK;
+}
+
+extern "C" int fs_sum_leading(int device, fs_stream_t stream_, const float* part, int S, long long n, float* out) {
+    if (!part || !out || S <= 0 || n <= 0) return FS_ERR_BAD_ARG;
+    FS_ENTER(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // small outputs: more partial groups per output so that the grid still covers the chip
+    if (n >= 32768) sum_leading_kernel<4><<<(unsigned)fs_div_up(n, 64), 256, 0, stream>>>(part, S, n, out);
+    else sum_leading_kernel<8><<<(unsigned)fs_div_up(n, 32), 256, 0, stream>>>(part, S, n, out);
     FS_RETURN_IF_LAUNCH_FAILED();
     return FS_OK;
 }

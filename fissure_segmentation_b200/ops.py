@@ -603,7 +603,7 @@ def _gram_f32(x):
         # split-K of the single GEMM runs at a fraction of the rate
         xv = x.view(S, P // S, -1)
         part = torch.bmm(xv.transpose(1, 2), xv) if x.dtype == torch.float32 else torch.bmm(xv.transpose(1, 2), xv, out_dtype=torch.float32)
-        return part.sum(dim=0)
+        return _sum_chunks(part)
     if x.dtype == torch.float32:
         return x.t() @ x
     return torch.mm(x.t(), x, out_dtype=torch.float32)
@@ -810,7 +810,7 @@ class _TableGemmFn(torch.autograd.Function):
                 while S < 128 and P % (2 * S) == 0 and P // (2 * S) >= 256:
                     S *= 2
                 if S > 1 and g.is_contiguous() and x.is_contiguous():
-                    gw = torch.bmm(g.view(S, P // S, -1).transpose(1, 2), x.view(S, P // S, -1)).sum(dim=0)
+                    gw = _sum_chunks(torch.bmm(g.view(S, P // S, -1).transpose(1, 2), x.view(S, P // S, -1)))
                 else:
                     gw = g.t() @ x
         return gx, gw, None
@@ -889,6 +889,17 @@ def final_linear_out(h, w, bias, perm, B, N):
     return _FinalLinearFn.apply(h, w, bias, perm.contiguous() if perm is not None else None, B, N)
 
 
+def _sum_chunks(part):
+    """(S, M, N) fp32 partial products -> (M, N): one coalesced pass (ATen's reduction over a short leading dimension of a
+    small tensor takes 8 us for 4 MB)."""
+    if not part.is_cuda or part.dtype != torch.float32 or not part.is_contiguous():
+        return part.sum(dim=0)
+    S, M, N = part.shape
+    out = torch.empty(M, N, dtype=torch.float32, device=part.device)
+    _lib.call("fs_sum_leading", part, part, S, M * N, out)
+    return out
+
+
 _ones_cache = {}
 
 
@@ -949,7 +960,7 @@ class _LinearFn(torch.autograd.Function):
             if S > 1 and g.is_contiguous() and x.is_contiguous() and g.is_cuda and g.shape[1] * x.shape[1] >= 16384:
                 gt, xv = g.view(S, P // S, -1).transpose(1, 2), x.view(S, P // S, -1)
                 part = torch.bmm(gt, xv) if g.dtype == torch.float32 else torch.bmm(gt, xv, out_dtype=torch.float32)
-                gw = part.sum(dim=0)
+                gw = _sum_chunks(part)
             elif g.dtype == torch.float32 or not g.is_cuda:
                 gw = g.float().t() @ x.float()
             else:

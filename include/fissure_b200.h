@@ -431,6 +431,10 @@ int fs_final_linear_bwd(int device, fs_stream_t stream, const void* h, int dtype
 int fs_edge_weight_table(int device, fs_stream_t stream, const float* w, int Cp, int C, float* out);
 int fs_edge_weight_table_bwd(int device, fs_stream_t stream, const float* g, int Cp, int C, float* dw);
 
+/* out [n] f32 = sum over s of part [S, n] f32 (fixed order): the reduction of the partial products of a row-chunked
+ * weight-gradient GEMM (dW = dY^T X issued as a batched GEMM over row chunks). */
+int fs_sum_leading(int device, fs_stream_t stream, const float* part, int S, long long n, float* out);
+
 /* ---------------------------------------------------------------- Chamfer ------------------ */
 
 /*
