@@ -8,6 +8,15 @@
 //     dW = S^T X + a colsum(X)^T + diag(b) W (X^T X)            one K x P x K Gram instead of C x P x K
 // so the P x C gradient (134 MB at P = 65536, C = 1024) is neither written nor read and y is not kept for backward.
 // The GEMMs stay library calls (host side, ops.py); the kernels here are the sparse parts and the coefficient vectors.
+//
+// Also in this file, the glue of the dense heads that used to be dozens of small ATen launches per step:
+//   cat_cast / split_cast        [x1 | x2 | x3] in the compute dtype in one pass, and the gradient back
+//   colsum_*                     deterministic column sums
+//   final_linear_fwd / bwd       last head layer (-> num_classes) fused with the B x classes x N output in caller order
+//   logits_out (+ adjoint)       the output transform alone
+//   edge_weight_table (+ adj.)   [W1 ; W2 - W1] from the EdgeConv weight
+//   sum_leading                  sum of the partial products of a row-chunked weight-gradient GEMM
+//   multi_copy                   a gradient bucket into the flat buffer in one launch
 #include "fs_common.cuh"
 
 namespace {
