@@ -32,3 +32,21 @@ def test_adam_step_peers_equals_adam_on_the_sum(lib, n, offset, world):
     assert torch.equal(p, p_ref) and torch.equal(m, m_ref) and torch.equal(v, v_ref)
     for b in bufs:                                         # nothing is written to a peer
         assert torch.isfinite(b).all()
+
+
+def test_multi_copy_moves_a_gradient_bucket(lib):
+    import ctypes
+    gen = torch.Generator().manual_seed(3)
+    sizes = [4, 1024 * 192, 7, 256 * 1216, 64 * 6, 1, 100000] + [33] * 40          # more than 32 tensors: two launches
+    srcs = [torch.randn(n, generator=gen).to(DEV) for n in sizes]
+    flat = torch.zeros(sum(sizes) + 3, device=DEV)
+    dsts, off = [], 1                                                                # odd offsets: no alignment assumed
+    for n in sizes:
+        dsts.append(flat[off:off + n]); off += n
+    n = len(srcs)
+    sp = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    dp = (ctypes.c_void_p * n)(*[t.data_ptr() for t in dsts])
+    cn = (ctypes.c_longlong * n)(*sizes)
+    _lib.call("fs_multi_copy_f32", flat, n, sp, dp, cn)
+    assert torch.equal(flat[1:1 + sum(sizes)], torch.cat(srcs))
+    assert float(flat[0]) == 0 and float(flat[1 + sum(sizes):].abs().sum()) == 0

@@ -248,3 +248,43 @@ def test_final_linear_out_matches_torch(lib, dtype, C_in, C_out, N):
         assert rel_err(a.grad.float(), b.grad.float()) < gt
         assert rel_err(wa.grad, wb.grad.float()) < 1e-5
         assert rel_err(ba.grad, bb.grad.float()) < 1e-5
+
+
+def test_small_head_helpers_match_torch(lib):
+    """fs_sum_leading, fs_edge_weight_table (+ adjoint) and the folded BatchNorm finalisation against their torch forms."""
+    from fissure_segmentation_b200 import _lib
+    gen = torch.Generator().manual_seed(12)
+    for S, M, N in ((16, 256, 256), (128, 128, 64), (3, 5, 7)):
+        part = torch.randn(S, M, N, generator=gen).to(DEV)
+        assert_close(ops._sum_chunks(part), part.double().sum(0).float(), 1e-6, 1e-5, "sum over chunks")
+    Cp, C = 64, 64
+    w = torch.randn(Cp, 2 * C, generator=gen).to(DEV).requires_grad_(True)
+    t = ops.edge_weight_table(w, C)
+    ref = torch.cat([w[:, :C], w[:, C:] - w[:, :C]], dim=0)
+    assert torch.equal(t, ref.detach())
+    g = torch.randn(2 * Cp, C, generator=gen).to(DEV)
+    (gw,) = torch.autograd.grad(t, w, g)
+    (gr,) = torch.autograd.grad(ref, w, g)
+    assert torch.equal(gw, gr)
+    # folded finalisation == fs_bn_finalize followed by the plain apply (coefficients, output, running statistics)
+    rows, Cn = 4096, 256
+    x = (torch.randn(rows, Cn, generator=gen) * 2 + 0.5).to(DEV).bfloat16()
+    res = []
+    for fused in (True, False):
+        bn = _bn(Cn, 7).to(DEV).train()
+        stats = torch.zeros(int(_lib.load().fs_stats_buffer_doubles(Cn)), dtype=torch.float64, device=DEV)
+        _lib.call("fs_colstats", x, x, 1, Cn, rows, Cn, None, 1, stats)
+        out = torch.empty_like(x)
+        coef = torch.empty(4 * Cn, device=DEV)
+        g32, b32 = bn.weight.detach().float(), bn.bias.detach().float()
+        if fused:
+            _lib.call("fs_bn_act_apply_fin", x, x, 1, Cn, rows, Cn, None, 1, stats, float(rows), g32, b32, bn.eps, bn.momentum,
+                      bn.running_mean, bn.running_var, bn.num_batches_tracked, coef, 0.2, out, 1, Cn)
+        else:
+            _lib.call("fs_bn_finalize", x, stats, float(rows), Cn, g32, b32, bn.eps, bn.momentum, coef, bn.running_mean,
+                      bn.running_var, bn.num_batches_tracked)
+            _lib.call("fs_bn_act_apply", x, x, 1, Cn, rows, Cn, None, 1, coef, 0.2, out, 1, Cn)
+        res.append((out.float(), coef.clone(), bn.running_mean.clone(), bn.running_var.clone(), int(bn.num_batches_tracked)))
+    for a, b, name in zip(res[0][:4], res[1][:4], ("out", "coef", "running_mean", "running_var")):
+        assert_close(a, b, 1e-6 if name != "out" else 1e-2, 1e-6 if name != "out" else 1e-2, name)
+    assert res[0][4] == res[1][4] == 1
